@@ -1,0 +1,211 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes binding of oracle/liborb_oracle.so (the plain-C restatement, oracle/orb_oracle.c + cv_prims.c).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .refio import KP_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborb_oracle.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+_lib = None
+
+
+def build(force=False):
+    """Compile the C restatement (and, when /root/reference is present, the verbatim reference)."""
+    if force:
+        subprocess.run(["make", "-C", HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.orb_oracle_create.restype = C.c_void_p
+        L.orb_oracle_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orb_oracle_destroy.argtypes = [C.c_void_p]
+        L.orb_oracle_scale_table.argtypes = [C.c_void_p, C.c_int, _fp]
+        L.orb_oracle_quota.argtypes = [C.c_void_p, _ip]
+        L.orb_oracle_umax.argtypes = [C.c_void_p, _ip]
+        L.orb_oracle_extract.restype = C.c_int
+        L.orb_oracle_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, _ip]
+        L.orb_oracle_level_size.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+        L.orb_oracle_level_plane.restype = C.c_void_p
+        L.orb_oracle_level_plane.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.orb_oracle_level_blur.restype = C.c_void_p
+        L.orb_oracle_level_blur.argtypes = [C.c_void_p, C.c_int]
+        L.orb_oracle_level_candidates.restype = C.c_int
+        L.orb_oracle_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_level_keypoints.restype = C.c_int
+        L.orb_oracle_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_distribute.restype = C.c_int
+        L.orb_oracle_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_ic_angle.restype = C.c_float
+        L.orb_oracle_ic_angle.argtypes = [C.c_void_p, C.c_size_t, _ip]
+        L.orb_oracle_descriptor.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
+        L.ocv_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        L.ocv_copy_make_border_reflect101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                         C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ocv_fast9_16_nms.restype = C.c_int
+        L.ocv_fast9_16_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ocv_fast9_16_best.restype = C.c_int
+        L.ocv_fast9_16_best.argtypes = [C.c_void_p, C.c_size_t]
+        L.ocv_gaussian_blur_7x7_s2_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ocv_fast_atan2.restype = C.c_float
+        L.ocv_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib = L
+    return _lib
+
+
+# ----- primitives ---------------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().ocv_resize_linear_u8(src.ctypes.data, src.shape[1], src.shape[0], src.strides[0], dst.ctypes.data, dw, dh, dw)
+    return dst
+
+
+def border101(src, b=19):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+    lib().ocv_copy_make_border_reflect101_u8(src.ctypes.data, w, h, src.strides[0], dst.ctypes.data, w + 2 * b, b, b, b, b)
+    return dst
+
+
+def fast_nms(img, th):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = ((w + 1) // 2) * ((h + 1) // 2) + 16
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().ocv_fast9_16_nms(img.ctypes.data, w, h, img.strides[0], th, xs.ctypes.data, ys.ctypes.data, sc.ctypes.data, cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def fast_best_map(img):
+    """best(p) for every pixel >= 3 px inside the image, 0 elsewhere (int16)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w), np.int16)
+    L = lib()
+    base = img.ctypes.data
+    for y in range(3, h - 3):
+        for x in range(3, w - 3):
+            out[y, x] = L.ocv_fast9_16_best(base + y * img.strides[0] + x, img.strides[0])
+    return out
+
+
+def gaussian_blur(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    dst = np.empty_like(img)
+    lib().ocv_gaussian_blur_7x7_s2_u8(img.ctypes.data, w, h, img.strides[0], dst.ctypes.data, w)
+    return dst
+
+
+def fast_atan2(y, x):
+    return float(lib().ocv_fast_atan2(float(y), float(x)))
+
+
+def distribute(xs, ys, scores, min_x, max_x, min_y, max_y, n_quota):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    scores = np.ascontiguousarray(scores, np.int32)
+    cap = len(xs) + 8
+    kept = np.empty(cap, np.int32)
+    n = lib().orb_oracle_distribute(xs.ctypes.data, ys.ctypes.data, scores.ctypes.data, len(xs), min_x, max_x, min_y,
+                                    max_y, n_quota, kept.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("distribute failed: %d" % n)
+    return kept[:n].copy()
+
+
+# ----- the extractor --------------------------------------------------------------------------------
+class OracleExtractor:
+    """Mirror of ORBextractor (reference inc/ORBextractor.h:44-111) on top of the C restatement."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, cell_w=30):
+        self._L = lib()
+        self._h = self._L.orb_oracle_create(nfeatures, scale_factor, nlevels, ini_th, min_th, cell_w)
+        if not self._h:
+            raise ValueError("bad oracle parameters")
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        tabs = []
+        for which in range(4):
+            t = np.empty(nlevels, np.float32)
+            self._L.orb_oracle_scale_table(self._h, which, t.ctypes.data_as(_fp))
+            tabs.append(t)
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2 = tabs
+        q = np.empty(nlevels, np.int32)
+        self._L.orb_oracle_quota(self._h, q.ctypes.data_as(_ip))
+        self.mnFeaturesPerLevel = q
+        u = np.empty(16, np.int32)
+        self._L.orb_oracle_umax(self._h, u.ctypes.data_as(_ip))
+        self.umax = u
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orb_oracle_destroy(self._h)
+            self._h = None
+
+    def extract(self, img, lap=(0, 0)):
+        """-> (ret, kps[KP_DTYPE], desc[n,32])"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        while True:
+            kps = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            ret = self._L.orb_oracle_extract(self._h, img.ctypes.data, w, h, img.strides[0], lap[0], lap[1],
+                                             kps.ctypes.data, desc.ctypes.data, cap, C.byref(n))
+            if ret < -1:
+                raise ValueError("oracle: level too small for the cell grid (UB in the reference)")
+            if n.value <= cap:
+                return ret, kps[:n.value].copy(), desc[:n.value].copy()
+            cap = n.value
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self._L.orb_oracle_level_size(self._h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_plane(self, level):
+        w, h = self.level_size(level)
+        pitch = C.c_size_t()
+        p = self._L.orb_oracle_level_plane(self._h, level, C.byref(pitch))
+        buf = (C.c_uint8 * ((h + 38) * pitch.value)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h + 38, pitch.value)[:, :w + 38].copy()
+
+    def level_blur(self, level):
+        w, h = self.level_size(level)
+        p = self._L.orb_oracle_level_blur(self._h, level)
+        if not p:
+            return None
+        buf = (C.c_uint8 * (h * w)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h, w).copy()
+
+    def level_candidates(self, level):
+        n = self._L.orb_oracle_level_candidates(self._h, level, None, None, None, 0)
+        xs, ys, sc = (np.empty(max(n, 1), np.int32) for _ in range(3))
+        self._L.orb_oracle_level_candidates(self._h, level, xs.ctypes.data, ys.ctypes.data, sc.ctypes.data, n)
+        return xs[:n], ys[:n], sc[:n]
+
+    def level_keypoints(self, level):
+        n = self._L.orb_oracle_level_keypoints(self._h, level, None, 0)
+        kps = np.zeros(max(n, 1), KP_DTYPE)
+        self._L.orb_oracle_level_keypoints(self._h, level, kps.ctypes.data, n)
+        return kps[:n]

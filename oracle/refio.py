@@ -1,0 +1,93 @@
+"""oracle/refio.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+File formats and subprocess helpers for the verbatim-reference binaries built by oracle/Makefile
+(`oracle/_ref/ref_extract`, `oracle/_ref/ref_extract_bump`; see oracle/ref_main.cpp).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import json
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BIN = os.path.join(HERE, "_ref", "ref_extract")
+REF_BIN_BUMP = os.path.join(HERE, "_ref", "ref_extract_bump")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def have_ref(bump=True):
+    return os.access(REF_BIN_BUMP if bump else REF_BIN, os.X_OK)
+
+
+def write_frames(path, frames):
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    if frames.ndim == 2:
+        frames = frames[None]
+    n, h, w = frames.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4i", 0x4642524F, n, w, h))
+        f.write(frames.tobytes())
+
+
+def read_results(path):
+    """-> list of dicts per frame: ret, kps (KP_DTYPE), desc (n,32), counts, level_kps [list], pyr [list]|None."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    magic, nframes, nlevels, dump = struct.unpack_from("<4i", buf, 0)
+    assert magic == 0x5242524F
+    off = 16
+    out = []
+    for _ in range(nframes):
+        ret, n = struct.unpack_from("<2i", buf, off)
+        off += 8
+        counts = np.frombuffer(buf, "<i4", nlevels, off).copy()
+        off += 4 * nlevels
+        kps = np.frombuffer(buf, KP_DTYPE, n, off).copy()
+        off += 28 * n
+        desc = np.frombuffer(buf, np.uint8, 32 * n, off).reshape(n, 32).copy()
+        off += 32 * n
+        lv = []
+        for c in counts:
+            lv.append(np.frombuffer(buf, KP_DTYPE, int(c), off).copy())
+            off += 28 * int(c)
+        pyr = None
+        if dump:
+            pyr = []
+            for _l in range(nlevels):
+                w, h = struct.unpack_from("<2i", buf, off)
+                off += 8
+                plane = np.frombuffer(buf, np.uint8, (w + 38) * (h + 38), off).reshape(h + 38, w + 38).copy()
+                off += (w + 38) * (h + 38)
+                pyr.append(plane)
+        out.append(dict(ret=ret, kps=kps, desc=desc, counts=counts, level_kps=lv, pyr=pyr))
+    assert off == len(buf)
+    return out
+
+
+def run_reference(frames, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 0), dump_pyr=False, bump=True):
+    """Run the unmodified reference on a stack of gray frames (n,h,w) u8."""
+    exe = REF_BIN_BUMP if bump else REF_BIN
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.orbf"), os.path.join(td, "out.orbr")
+        write_frames(fin, frames)
+        cmd = [exe, "run", fin, fout, str(nfeatures), repr(float(scale)), str(nlevels), str(ini), str(mn),
+               str(lap[0]), str(lap[1]), "1" if dump_pyr else "0"]
+        subprocess.run(cmd, check=True)
+        return read_results(fout)
+
+
+def bench_reference(frames, threads, seconds, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 0)):
+    """Time the unmodified reference (normal allocator), one extractor + one frame per thread."""
+    with tempfile.TemporaryDirectory() as td:
+        fin = os.path.join(td, "in.orbf")
+        write_frames(fin, frames)
+        cmd = [REF_BIN, "bench", fin, str(threads), repr(float(seconds)), str(nfeatures), repr(float(scale)),
+               str(nlevels), str(ini), str(mn), str(lap[0]), str(lap[1])]
+        r = subprocess.run(cmd, check=True, capture_output=True, text=True)
+        return json.loads(r.stdout.strip().splitlines()[-1])
