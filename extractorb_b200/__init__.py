@@ -1,0 +1,265 @@
+"""extractorb_b200 -- B200-native ORB extraction path (sm_100a CUDA behind the C-ABI of include/orbx.h).
+
+This package is a thin ctypes view of ``libextractorb_cuda.so`` for tests, benchmarks and Python callers.
+The reference's own interface is C++ (``ORB_SLAM3::ORBextractor``, reference inc/ORBextractor.h:44-111);
+its drop-in lives in include/ORBextractor.h + extractorb_b200/csrc/ORBextractor.cpp.  ``ORBextractor``
+below mirrors that class (same constructor arguments, member names and return conventions).
+
+There is no CPU fallback: importing works anywhere, but constructing an extractor without the built
+library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_PROFILE = 1
+
+# cv::KeyPoint layout (28 bytes)
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class OrbxParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("cell_size", C.c_int32),
+                ("max_batch", C.c_int32), ("cand_per_cell", C.c_int32), ("flags", C.c_int32)]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("orbx error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(HERE, "libextractorb_cuda.so")
+
+
+def load_library():
+    """Load libextractorb_cuda.so (built in-tree by extractorb_b200.build).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise OrbxError(-9, "%s not built (run `python -m extractorb_b200.build`); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.orbx_status_string.restype = C.c_char_p
+    L.orbx_status_string.argtypes = [i32]
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_last_error.argtypes = [vp]
+    L.orbx_create.argtypes = [C.POINTER(OrbxParams), i32, C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_destroy.restype = None
+    L.orbx_get_tables.argtypes = [vp] + [vp] * 6
+    L.orbx_max_keypoints.argtypes = [vp, i32, i32]
+    L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, i32, i32, vp, vp, i32, vp, i32, vp]
+    L.orbx_compute_pyramid.argtypes = [vp, vp, i32, i32, sz]
+    L.orbx_compute_keypoints_octtree.argtypes = [vp]
+    L.orbx_distribute_octtree.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32)]
+    L.orbx_get_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.orbx_get_pyramid_level.argtypes = [vp, i32, i32, vp, sz, i32]
+    L.orbx_get_level_keypoints.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.orbx_get_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32)]
+    L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, sz]
+    L.orbx_stage_times.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    L.orbx_launch_count.restype = C.c_int64
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_get_stream.restype = vp
+    L.orbx_get_stream.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM3::ORBextractor (reference inc/ORBextractor.h:44-111) over the C-ABI.
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) as in the reference
+    (src/orb_extractor/ORBextractor.cc:408-411); keyword-only extras configure the GPU side.
+    """
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, *, device=0, max_batch=1,
+                 cell_size=30, cand_per_cell=0, profile=False):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        prm = OrbxParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, cell_size, max_batch, cand_per_cell,
+                         FLAG_PROFILE if profile else 0)
+        rc = self._L.orbx_create(C.byref(prm), device, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise OrbxError(rc, self._L.orbx_status_string(rc).decode())
+        self.nfeatures, self.scaleFactor, self.nlevels = nfeatures, float(np.float32(scaleFactor)), nlevels
+        self.iniThFAST, self.minThFAST = iniThFAST, minThFAST
+        self.device, self.max_batch = device, max_batch
+        t = [np.empty(nlevels, np.float32) for _ in range(4)]
+        q = np.empty(nlevels, np.int32)
+        u = np.empty(16, np.int32)
+        self._check(self._L.orbx_get_tables(self._h, *[a.ctypes.data for a in t], q.ctypes.data, u.ctypes.data))
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2 = t
+        self.mnFeaturesPerLevel, self.umax = q, u
+
+    # -- reference accessors (inc/ORBextractor.h:63-83) --
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self.mvScaleFactor.copy()
+    def GetInverseScaleFactors(self): return self.mvInvScaleFactor.copy()
+    def GetScaleSigmaSquares(self): return self.mvLevelSigma2.copy()
+    def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2.copy()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OrbxError(rc, "%s: %s" % (self._L.orbx_status_string(rc).decode(), self._L.orbx_last_error(self._h).decode()))
+
+    def max_keypoints(self, width, height):
+        n = self._L.orbx_max_keypoints(self._h, width, height)
+        if n < 0:
+            self._check(n)
+        return n
+
+    # -- operator() (ORBextractor.cc:1078-1162) --
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        """-> (ret, keypoints[KP_DTYPE], descriptors[n,32]).  `mask` is ignored like in the reference.
+        An empty image returns (-1, empty, empty) as the reference does (:1083)."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise ValueError("image must be CV_8UC1 (2-D uint8)")  # reference: assert(type == CV_8UC1), :1087
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        cap = self.max_keypoints(w, h)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        self._check(self._L.orbx_extract(self._h, image.ctypes.data, w, h, image.strides[0], int(vLappingArea[0]),
+                                         int(vLappingArea[1]), kps.ctypes.data, desc.ctypes.data, cap, C.byref(n), C.byref(mono)))
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch_host(self, frames, vLappingArea=(0, 0)):
+        """frames: (F,H,W) uint8 host array -> (counts[F,2]={n,mono}, kps[F,cap], desc[F,cap,32])."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        F, h, w = frames.shape
+        cap = self.max_keypoints(w, h)
+        kps = np.zeros((F, cap), KP_DTYPE)
+        desc = np.zeros((F, cap, 32), np.uint8)
+        counts = np.zeros((F, 2), np.int32)
+        self._check(self._L.orbx_extract_batch(self._h, frames.ctypes.data, MEM_HOST, F, w, h, w, w * h, int(vLappingArea[0]),
+                                               int(vLappingArea[1]), kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data,
+                                               MEM_HOST, None))
+        return counts, kps, desc
+
+    def extract_batch_raw(self, images_ptr, in_mem, n_frames, width, height, row_stride, frame_stride, lap, kps_ptr, desc_ptr,
+                          cap_per_frame, counts_ptr, out_mem, stream=None):
+        """Direct call of orbx_extract_batch with raw pointers (device or host)."""
+        self._check(self._L.orbx_extract_batch(self._h, images_ptr, in_mem, n_frames, width, height, row_stride, frame_stride,
+                                               int(lap[0]), int(lap[1]), kps_ptr, desc_ptr, cap_per_frame, counts_ptr, out_mem,
+                                               stream))
+
+    # -- stage-wise public methods of the reference (inc/ORBextractor.h:89-92) --
+    def ComputePyramid(self, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w = image.shape
+        self._check(self._L.orbx_compute_pyramid(self._h, image.ctypes.data, w, h, image.strides[0]))
+
+    def ComputeKeyPointsOctTree(self):
+        """-> allKeypoints: list (per level) of KP_DTYPE arrays in level coordinates, angle set."""
+        self._check(self._L.orbx_compute_keypoints_octtree(self._h))
+        return [self.level_keypoints(l) for l in range(self.nlevels)]
+
+    def DistributeOctTree(self, keys, minX, maxX, minY, maxY, N, level=0):
+        keys = np.ascontiguousarray(keys, KP_DTYPE)
+        cap = max(N + 2, 4 * max(1, int(round((maxX - minX) / max(1, maxY - minY))))) + 8
+        out = np.zeros(cap, KP_DTYPE)
+        n = C.c_int(0)
+        self._check(self._L.orbx_distribute_octtree(self._h, keys.ctypes.data, len(keys), minX, maxX, minY, maxY, N,
+                                                    out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    # -- state of the last extraction --
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._L.orbx_get_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def pyramid_level(self, level, frame=0, with_border=False):
+        """mvImagePyramid[level] (inc/ORBextractor.h:85); with_border adds the 19-px reflect-101 frame."""
+        w, h = self.level_size(level)
+        b = 19 if with_border else 0
+        out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+        self._check(self._L.orbx_get_pyramid_level(self._h, frame, level, out.ctypes.data, out.strides[0], int(with_border)))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    def GetPyramid(self):
+        return self.mvImagePyramid
+
+    def blurred_level(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        self._check(self._L.orbx_get_blurred_level(self._h, frame, level, out.ctypes.data, out.strides[0]))
+        return out
+
+    def level_keypoints(self, level, frame=0):
+        n = C.c_int(0)
+        self._check(self._L.orbx_get_level_keypoints(self._h, frame, level, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), KP_DTYPE)
+        self._check(self._L.orbx_get_level_keypoints(self._h, frame, level, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def level_candidates(self, level, frame=0):
+        """FAST candidates sorted into the reference's emission order -> (x, y, score) int32 arrays."""
+        n = C.c_int(0)
+        self._check(self._L.orbx_get_level_candidates(self._h, frame, level, None, None, None, None, 0, C.byref(n)))
+        m = max(n.value, 1)
+        xs, ys, sc = (np.zeros(m, np.int32) for _ in range(3))
+        od = np.zeros(m, np.uint32)
+        self._check(self._L.orbx_get_level_candidates(self._h, frame, level, xs.ctypes.data, ys.ctypes.data, sc.ctypes.data,
+                                                      od.ctypes.data, n.value, C.byref(n)))
+        order = np.argsort(od[:n.value], kind="stable")
+        return xs[:n.value][order], ys[:n.value][order], sc[:n.value][order]
+
+    def stage_times(self):
+        """-> (dict stage -> ms since last call, kernel launches since last call); needs profile=True."""
+        ms = np.zeros(len(STAGE_NAMES), np.float32)
+        n = C.c_int64(0)
+        self._check(self._L.orbx_stage_times(self._h, ms.ctypes.data, C.byref(n)))
+        return dict(zip(STAGE_NAMES, ms.tolist())), n.value
+
+    def launch_count(self):
+        return int(self._L.orbx_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._L.orbx_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._L.orbx_get_stream(self._h)

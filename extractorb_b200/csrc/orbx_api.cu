@@ -1,0 +1,828 @@
+// extractorb_b200/csrc/orbx_api.cu -- host side of libextractorb_cuda.so: constructor tables, per-size
+// plan, workspace in HBM, launch orchestration and the extern "C" boundary declared in include/orbx.h.
+//
+// Reference being replaced: ORB_SLAM3::ORBextractor (/root/reference/src/orb_extractor/ORBextractor.cc,
+// twin ORBExtractor.cpp).  Line citations below refer to ORBextractor.cc.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_kernels.cuh"
+
+static const int8_t kPatternHost[1024] = {
+#include "orb_pattern.inc"
+};
+
+namespace {
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }      // cvRound: round half to even
+inline int cv_round_d(double v) { return (int)lrint(v); }
+inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+inline int cv_ceil_f(float v) { int i = (int)v; return i + (i < v); }
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct PlanEntry {
+    OrbxPlan plan;
+    std::vector<int2> xtab, ytab;
+    std::vector<OrbxCell> cells;
+    int2* d_xtab = nullptr;
+    int2* d_ytab = nullptr;
+    OrbxCell* d_cells = nullptr;
+    long long pyr_stride = 0, blur_stride = 0, cand_stride = 0;
+    size_t fast_smem = 0, qt_smem = 0;
+    int max_cells_dim = 0;
+    int blur_tiles = 0;
+};
+
+struct StageEvents { cudaEvent_t ev[ORBX_NUM_STAGES + 1]; };
+
+}  // namespace
+
+struct OrbxHandle {
+    OrbxParams prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // constructor tables (:408-475)
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    int umax[16];
+    OrbxFloatConsts fc;
+    int cand_per_cell = 64;
+    // plans keyed by image size
+    std::map<std::pair<int, int>, PlanEntry*> plans;
+    PlanEntry* cur = nullptr;      // plan of the resident frames
+    int resident_frames = 0;
+    // workspace (sized for ws_frames frames of ws_plan)
+    PlanEntry* ws_plan = nullptr;
+    int ws_frames = 0;
+    OrbxWs ws{};
+    int8_t* d_pattern = nullptr;
+    uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
+    void* d_out = nullptr; size_t d_out_bytes = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned
+    // profiling
+    std::vector<StageEvents> events;
+    size_t events_used = 0;
+    double stage_ms[ORBX_NUM_STAGES] = {0, 0, 0, 0, 0};
+    int64_t stage_launches = 0;
+    int64_t total_launches = 0;
+    // standalone DistributeOctTree scratch
+    PlanEntry* dist_plan = nullptr;
+};
+
+namespace {
+
+int fail(OrbxHandle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define ORBX_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            char buf_[512];                                                                          \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(h, ORBX_ERR_CUDA, buf_);                                                     \
+        }                                                                                            \
+    } while (0)
+
+// ORBextractor::ORBextractor, :408-475.  Float/double mix reproduced literally.
+void build_ctor_tables(OrbxHandle* h) {
+    const int L = h->prm.nlevels;
+    const double scaleFactor = (double)h->prm.scale_factor;  // double member initialised from float (inc/ORBextractor.h:98)
+    h->sf.assign(L, 1.f); h->inv_sf.assign(L, 1.f); h->sigma2.assign(L, 1.f); h->inv_sigma2.assign(L, 1.f);
+    for (int i = 1; i < L; ++i) {
+        h->sf[i] = (float)(h->sf[i - 1] * scaleFactor);
+        h->sigma2[i] = h->sf[i] * h->sf[i];
+    }
+    for (int i = 0; i < L; ++i) {
+        h->inv_sf[i] = 1.0f / h->sf[i];
+        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    }
+    h->quota.assign(L, 0);
+    float factor = (float)(1.0f / scaleFactor);
+    float nDesired = h->prm.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
+    int sum = 0;
+    for (int l = 0; l < L - 1; ++l) {
+        h->quota[l] = cv_round_f(nDesired);
+        sum += h->quota[l];
+        nDesired *= factor;
+    }
+    h->quota[L - 1] = std::max(h->prm.nfeatures - sum, 0);
+    // umax, :459-474
+    int v, v0;
+    const int vmax = cv_floor_f(ORBX_HALF_PATCH * sqrtf(2.f) / 2 + 1);
+    const int vmin = cv_ceil_f(ORBX_HALF_PATCH * sqrtf(2.f) / 2);
+    const double hp2 = ORBX_HALF_PATCH * ORBX_HALF_PATCH;
+    for (v = 0; v < 16; ++v) h->umax[v] = 0;
+    for (v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = ORBX_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+    // cv::fastAtan2 constants (float products, as OpenCV computes them) and factorPI (:104)
+    const float s = (float)(180.0 / 3.1415926535897932384626433832795);
+    h->fc.atan_p1 = 0.9997878412794807f * s;
+    h->fc.atan_p3 = -0.3258083974640975f * s;
+    h->fc.atan_p5 = 0.1555786518463281f * s;
+    h->fc.atan_p7 = -0.04432655554792128f * s;
+    h->fc.atan_eps = (float)DBL_EPSILON;
+    h->fc.deg2rad = (float)(3.1415926535897932384626433832795 / 180.f);
+}
+
+// cv::resize INTER_LINEAR coefficient tables (per axis), OpenCV resize.cpp model.
+void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cv_floor_f(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        const int a0 = cv_round_f((1.f - f) * 2048.f), a1 = cv_round_f(f * 2048.f);
+        out.push_back(make_int2(s, (a0 & 0xffff) | (a1 << 16)));
+    }
+}
+
+void free_plan(PlanEntry* p) {
+    if (!p) return;
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells);
+    delete p;
+}
+
+int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
+    const int L = h->prm.nlevels;
+    const float W = (float)(h->prm.cell_size > 0 ? h->prm.cell_size : 30);   // :777
+    PlanEntry* pe = new PlanEntry();
+    OrbxPlan& P = pe->plan;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = L; P.width = width; P.height = height;
+    P.ini_th = std::min(std::max(h->prm.ini_th_fast, 0), 255);   // cv::FAST clamps the threshold
+    P.min_th = std::min(std::max(h->prm.min_th_fast, 0), 255);
+    for (int i = 0; i < 16; ++i) P.umax[i] = h->umax[i];
+    long long plane_off = 0, blur_off = 0, cand_off = 0;
+    int kp_off = 0, maxcw = 7, maxch = 7, qt_nc = 8;
+    for (int l = 0; l < L; ++l) {
+        OrbxLevel& V = P.lv[l];
+        V.w = cv_round_f((float)width * h->inv_sf[l]);     // :1171
+        V.h = cv_round_f((float)height * h->inv_sf[l]);
+        if (V.w > ORBX_MAX_LEVEL_DIM || V.h > ORBX_MAX_LEVEL_DIM) { delete pe; return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "level larger than 4127 px"); }
+        if (V.w <= 2 * ORBX_EDGE || V.h <= 2 * ORBX_EDGE) { delete pe; return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "pyramid level smaller than the 19-px border"); }
+        V.pitch = (int)align_up(ORBX_PADL + V.w + ORBX_EDGE, 64);
+        V.plane_rows = V.h + 2 * ORBX_EDGE;
+        V.plane_off = plane_off;
+        plane_off += align_up((long long)V.pitch * V.plane_rows, 256);
+        V.blur_pitch = (int)align_up(V.w, 16);
+        V.blur_off = blur_off;
+        blur_off += align_up((long long)V.blur_pitch * V.h, 256);
+        if (l > 0) {
+            const OrbxLevel& S = P.lv[l - 1];
+            V.xtab_off = (int)pe->xtab.size();
+            V.ytab_off = (int)pe->ytab.size();
+            if (S.w == 2 * V.w && S.h == 2 * V.h) {       // OpenCV: exact 2x decimation -> INTER_AREA fast path
+                for (int x = 0; x < V.w; ++x) pe->xtab.push_back(make_int2(2 * x, -1));
+                for (int y = 0; y < V.h; ++y) pe->ytab.push_back(make_int2(2 * y, 0));
+            } else {
+                linear_axis_table(S.w, V.w, pe->xtab);
+                linear_axis_table(S.h, V.h, pe->ytab);
+            }
+        }
+        // FAST cell grid, :781-814
+        const int minBX = ORBX_FAST_BORDER, minBY = ORBX_FAST_BORDER;
+        const int maxBX = V.w - ORBX_FAST_BORDER, maxBY = V.h - ORBX_FAST_BORDER;
+        const float fwidth = (float)(maxBX - minBX), fheight = (float)(maxBY - minBY);
+        V.nCols = (int)(fwidth / W); V.nRows = (int)(fheight / W);
+        if (V.nCols < 1 || V.nRows < 1) { delete pe; return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "pyramid level narrower than one FAST cell (division by zero in the reference, ORBextractor.cc:794)"); }
+        V.wCell = (int)ceilf(fwidth / V.nCols); V.hCell = (int)ceilf(fheight / V.nRows);
+        V.cell_off = (int)pe->cells.size();
+        for (int i = 0; i < V.nRows; ++i) {
+            const float iniY = (float)(minBY + i * V.hCell);
+            float maxY = iniY + V.hCell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = (float)maxBY;
+            for (int j = 0; j < V.nCols; ++j) {
+                const float iniX = (float)(minBX + j * V.wCell);
+                float maxX = iniX + V.wCell + 6;
+                if (iniX >= maxBX - 6) continue;          // -6 here vs -3 for rows: reference quirk, kept
+                if (maxX > maxBX) maxX = (float)maxBX;
+                const int cw = (int)maxX - (int)iniX, ch = (int)maxY - (int)iniY;
+                if (cw < 7 || ch < 7) continue;           // cv::FAST finds nothing in images < 7 px
+                if (cw > ORBX_MAX_CELL_DIM || ch > ORBX_MAX_CELL_DIM) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large (cell image > 127 px)"); }
+                OrbxCell c;
+                c.x0 = (uint16_t)(int)iniX; c.y0 = (uint16_t)(int)iniY; c.cw = (uint8_t)cw; c.ch = (uint8_t)ch;
+                c.level = (uint8_t)l; c.pad = 0;
+                c.ordbase = (uint32_t)(i * V.nCols + j) << ORBX_ORD_CELL_SHIFT;
+                c.xoff = (uint16_t)(j * V.wCell); c.yoff = (uint16_t)(i * V.hCell);
+                if ((long long)V.nRows * V.nCols >= (1 << (32 - ORBX_ORD_CELL_SHIFT))) { delete pe; return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "too many cells"); }
+                pe->cells.push_back(c);
+                maxcw = std::max(maxcw, cw); maxch = std::max(maxch, ch);
+            }
+        }
+        V.ncells = (int)pe->cells.size() - V.cell_off;
+        // quadtree, :548-550
+        V.N = h->quota[l];
+        V.nIni = (int)roundf((float)(maxBX - minBX) / (maxBY - minBY));
+        if (V.nIni < 1) { delete pe; return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "aspect ratio < 0.5 (nIni == 0 is UB in the reference, ORBextractor.cc:548)"); }
+        V.hX = (float)(maxBX - minBX) / V.nIni;
+        V.span_y = maxBY - minBY;
+        const long long worst = (long long)std::max(V.ncells, 1) * ((V.wCell + 1) / 2) * ((V.hCell + 1) / 2);
+        long long cap = std::max<long long>(1024, (long long)V.ncells * h->cand_per_cell);
+        cap = std::min(cap, std::max<long long>(worst, 16));
+        cap = align_up(cap, 4);
+        if (cap >= (1 << 24)) { delete pe; return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "candidate capacity exceeds 2^24"); }
+        V.cand_cap = (int)cap;
+        V.cand_off = cand_off;
+        cand_off += cap;
+        V.kp_cap = std::max(V.N + 2, 4 * V.nIni) + 2;
+        V.kp_off = kp_off;
+        kp_off += V.kp_cap;
+        qt_nc = std::max(qt_nc, V.kp_cap + 2);
+        V.sf = h->sf[l];
+        V.kp_size = (float)(int)(31 * h->sf[l]);           // scaledPatchSize, :872
+    }
+    P.ncells_total = (int)pe->cells.size();
+    P.kp_total = kp_off;
+    P.qt_nc = qt_nc;
+    P.fast_tp = (int)align_up(maxcw + 6, 4);
+    P.fast_trows = maxch;
+    P.fast_qcap = (int)align_up((long long)(maxcw - 6) * (maxch - 6), 2);
+    pe->pyr_stride = align_up(plane_off, 256);
+    pe->blur_stride = align_up(blur_off, 256);
+    pe->cand_stride = align_up(cand_off, 4);
+    pe->fast_smem = (size_t)ORBX_FAST_WARPS * (2 * (size_t)P.fast_tp * P.fast_trows + 2 * (size_t)P.fast_qcap);
+    pe->qt_smem = (size_t)qt_nc * 64;
+    if (pe->qt_smem > 200 * 1024 || qt_nc > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "nfeatures per level too large for the quadtree kernel's shared memory"); }
+    if (pe->fast_smem > 200 * 1024) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
+    int tiles = 0;
+    for (int l = 0; l < L; ++l)
+        tiles += ((P.lv[l].w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW) * ((P.lv[l].h + ORBX_BLUR_TH - 1) / ORBX_BLUR_TH);
+    pe->blur_tiles = tiles;
+    // device tables
+    const size_t nx = std::max<size_t>(pe->xtab.size(), 1), ny = std::max<size_t>(pe->ytab.size(), 1);
+    ORBX_CUDA(cudaMalloc(&pe->d_xtab, nx * sizeof(int2)));
+    ORBX_CUDA(cudaMalloc(&pe->d_ytab, ny * sizeof(int2)));
+    ORBX_CUDA(cudaMalloc(&pe->d_cells, std::max<size_t>(pe->cells.size(), 1) * sizeof(OrbxCell)));
+    if (!pe->xtab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_xtab, pe->xtab.data(), pe->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    if (!pe->ytab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_ytab, pe->ytab.data(), pe->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    if (!pe->cells.empty()) ORBX_CUDA(cudaMemcpy(pe->d_cells, pe->cells.data(), pe->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
+    *out = pe;
+    return ORBX_OK;
+}
+
+void free_workspace(OrbxHandle* h) {
+    cudaFree(h->ws.pyr); cudaFree(h->ws.blur); cudaFree(h->ws.cand); cudaFree(h->ws.keynode);
+    cudaFree(h->ws.kprec); cudaFree(h->ws.cand_count); cudaFree(h->ws.level_count); cudaFree(h->ws.flags);
+    memset(&h->ws, 0, sizeof(h->ws));
+    h->ws_plan = nullptr; h->ws_frames = 0; h->resident_frames = 0; h->cur = nullptr;
+}
+
+int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
+    if (h->ws_plan == pe && h->ws_frames >= frames) return ORBX_OK;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    free_workspace(h);
+    const OrbxPlan& P = pe->plan;
+    OrbxWs& w = h->ws;
+    ORBX_CUDA(cudaMalloc(&w.pyr, (size_t)pe->pyr_stride * frames));
+    ORBX_CUDA(cudaMalloc(&w.blur, (size_t)pe->blur_stride * frames));
+    ORBX_CUDA(cudaMalloc(&w.cand, (size_t)pe->cand_stride * frames * sizeof(uint2)));
+    ORBX_CUDA(cudaMalloc(&w.keynode, (size_t)pe->cand_stride * frames * sizeof(uint16_t)));
+    ORBX_CUDA(cudaMalloc(&w.kprec, (size_t)P.kp_total * frames * sizeof(OrbxKpRec)));
+    ORBX_CUDA(cudaMalloc(&w.cand_count, (size_t)P.nlevels * frames * sizeof(int)));
+    ORBX_CUDA(cudaMalloc(&w.level_count, (size_t)P.nlevels * frames * sizeof(int2)));
+    ORBX_CUDA(cudaMalloc(&w.flags, (size_t)frames * sizeof(int)));
+    w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
+    w.kp_stride = P.kp_total;
+    w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.pattern = h->d_pattern;
+    h->ws_plan = pe; h->ws_frames = frames;
+    return ORBX_OK;
+}
+
+int get_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
+    auto key = std::make_pair(width, height);
+    auto it = h->plans.find(key);
+    if (it != h->plans.end()) { *out = it->second; return ORBX_OK; }
+    PlanEntry* pe = nullptr;
+    int rc = build_plan(h, width, height, &pe);
+    if (rc != ORBX_OK) return rc;
+    h->plans[key] = pe;
+    *out = pe;
+    return ORBX_OK;
+}
+
+void drop_plans(OrbxHandle* h) {
+    free_workspace(h);
+    for (auto& kv : h->plans) free_plan(kv.second);
+    h->plans.clear();
+}
+
+enum { STAGES_PYRAMID = 1, STAGES_KEYPOINTS = 2, STAGES_ALL = 3 };
+
+// Launch the stages for `nf` device-resident frames.  Outputs (device pointers, may be NULL) are written
+// at frame index frame_out0 + f.
+int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
+                 long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
+                 int32_t* d_counts, int frame_out0, int stages) {
+    OrbxPlan P = pe->plan;
+    P.lap0 = lap0; P.lap1 = lap1;
+    const OrbxWs& ws = h->ws;
+    const bool prof = (h->prm.flags & ORBX_FLAG_PROFILE) != 0;
+    StageEvents* se = nullptr;
+    if (prof) {
+        if (h->events_used == h->events.size()) {
+            StageEvents e;
+            for (auto& x : e.ev) ORBX_CUDA(cudaEventCreate(&x));
+            h->events.push_back(e);
+        }
+        se = &h->events[h->events_used++];
+        ORBX_CUDA(cudaEventRecord(se->ev[0], st));
+    }
+    int64_t launches = 0;
+    if (stages & STAGES_PYRAMID) {
+        const dim3 blk(64, 4);
+        {
+            const OrbxLevel& V = P.lv[0];
+            const dim3 grd((V.pitch / 4 + 63) / 64, (V.plane_rows + 3) / 4, nf);
+            k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride);
+            ++launches;
+        }
+        for (int l = 1; l < P.nlevels; ++l) {
+            const OrbxLevel& V = P.lv[l];
+            const dim3 grd((V.pitch / 4 + 63) / 64, (V.plane_rows + 3) / 4, nf);
+            k_pyr_resize<<<grd, blk, 0, st>>>(P, ws, l);
+            ++launches;
+        }
+    }
+    if (se) ORBX_CUDA(cudaEventRecord(se->ev[1], st));
+    if (stages & STAGES_KEYPOINTS) {
+        ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
+        ORBX_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)nf * sizeof(int), st));
+        const long long warps = (long long)P.ncells_total * nf;
+        const unsigned blocks = (unsigned)((warps + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS);
+        k_fast_cells<<<blocks, ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, nf);
+        ++launches;
+        if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
+        k_octree<<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);
+        ++launches;
+        if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
+        k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws);
+        ++launches;
+        if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
+        k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        ++launches;
+        if (se) ORBX_CUDA(cudaEventRecord(se->ev[5], st));
+    } else if (se) {
+        for (int i = 2; i <= ORBX_NUM_STAGES; ++i) ORBX_CUDA(cudaEventRecord(se->ev[i], st));
+    }
+    ORBX_CUDA(cudaGetLastError());
+    h->stage_launches += launches;
+    h->total_launches += launches;
+    h->cur = pe;
+    h->resident_frames = nf;
+    return ORBX_OK;
+}
+
+int collect_events(OrbxHandle* h) {
+    for (size_t i = 0; i < h->events_used; ++i)
+        for (int s = 0; s < ORBX_NUM_STAGES; ++s) {
+            float ms = 0.f;
+            ORBX_CUDA(cudaEventElapsedTime(&ms, h->events[i].ev[s], h->events[i].ev[s + 1]));
+            h->stage_ms[s] += ms;
+        }
+    h->events_used = 0;
+    return ORBX_OK;
+}
+
+int ensure_bytes(OrbxHandle* h, void** p, size_t* have, size_t need, bool pinned_host) {
+    if (*have >= need) return ORBX_OK;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    if (pinned_host) { if (*p) cudaFreeHost(*p); } else { if (*p) cudaFree(*p); }
+    *p = nullptr; *have = 0;
+    if (pinned_host) ORBX_CUDA(cudaMallocHost(p, need)); else ORBX_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return ORBX_OK;
+}
+
+int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
+    if (pe->fast_smem > 48 * 1024)
+        ORBX_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->fast_smem));
+    if (pe->qt_smem > 48 * 1024)
+        ORBX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+    return ORBX_OK;
+}
+
+// Did any frame of the last group overflow its candidate workspace?
+int check_overflow(OrbxHandle* h, int nf, bool* overflow) {
+    std::vector<int> flags(nf);
+    ORBX_CUDA(cudaMemcpy(flags.data(), h->ws.flags, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost));
+    *overflow = false;
+    for (int f : flags) if (f & 1) *overflow = true;
+    return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orbx_status_string(int s) {
+    switch (s) {
+        case ORBX_OK: return "ok";
+        case ORBX_ERR_EMPTY_IMAGE: return "empty image";
+        case ORBX_ERR_BAD_ARGUMENT: return "bad argument";
+        case ORBX_ERR_LEVEL_TOO_SMALL: return "pyramid level too small";
+        case ORBX_ERR_IMAGE_TOO_LARGE: return "image too large";
+        case ORBX_ERR_CUDA: return "CUDA error";
+        case ORBX_ERR_CAPACITY: return "output capacity too small";
+        case ORBX_ERR_CANDIDATE_OVERFLOW: return "FAST candidate overflow";
+        case ORBX_ERR_NO_FRAME: return "no resident frame";
+        case ORBX_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+
+const char* orbx_last_error(const OrbxHandle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
+    if (!prm || !out) return ORBX_ERR_BAD_ARGUMENT;
+    *out = nullptr;
+    if (prm->nlevels < 1 || prm->nlevels > ORBX_MAX_LEVELS || prm->nfeatures < 0 || !(prm->scale_factor > 1.0f) ||
+        prm->cell_size < 0 || prm->cell_size > 60 || prm->max_batch < 0)
+        return ORBX_ERR_BAD_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ORBX_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return ORBX_ERR_BAD_ARGUMENT;
+    OrbxHandle* h = new OrbxHandle();
+    h->prm = *prm;
+    if (h->prm.cell_size == 0) h->prm.cell_size = 30;
+    if (h->prm.max_batch == 0) h->prm.max_batch = 1;
+    h->cand_per_cell = prm->cand_per_cell > 0 ? prm->cand_per_cell : 64;
+    h->device = device;
+    build_ctor_tables(h);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern, sizeof(kPatternHost));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete h; return ORBX_ERR_CUDA; }
+    *out = h;
+    return ORBX_OK;
+}
+
+void orbx_destroy(OrbxHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_plans(h);
+    free_plan(h->dist_plan);
+    cudaFree(h->d_pattern); cudaFree(h->d_in); cudaFree(h->d_out);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int orbx_get_tables(const OrbxHandle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* fpl, int32_t* umax16) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    const size_t L = (size_t)h->prm.nlevels;
+    if (scale) memcpy(scale, h->sf.data(), L * sizeof(float));
+    if (inv_scale) memcpy(inv_scale, h->inv_sf.data(), L * sizeof(float));
+    if (sigma2) memcpy(sigma2, h->sigma2.data(), L * sizeof(float));
+    if (inv_sigma2) memcpy(inv_sigma2, h->inv_sigma2.data(), L * sizeof(float));
+    if (fpl) memcpy(fpl, h->quota.data(), L * sizeof(int32_t));
+    if (umax16) memcpy(umax16, h->umax, 16 * sizeof(int32_t));
+    return ORBX_OK;
+}
+
+int orbx_max_keypoints(const OrbxHandle* hc, int width, int height) {
+    OrbxHandle* h = const_cast<OrbxHandle*>(hc);
+    if (!h || width <= 0 || height <= 0) return ORBX_ERR_BAD_ARGUMENT;
+    if (cudaSetDevice(h->device) != cudaSuccess) return ORBX_ERR_CUDA;
+    PlanEntry* pe = nullptr;
+    int rc = get_plan(h, width, height, &pe);
+    if (rc != ORBX_OK) return rc;
+    return pe->plan.kp_total;
+}
+
+int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height,
+                       size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps, uint8_t* desc,
+                       int cap_per_frame, int32_t* counts, int out_mem, void* stream) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (!images || width <= 0 || height <= 0 || n_frames <= 0) return fail(h, ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (row_stride < (size_t)width || cap_per_frame < 0 || (n_frames > 1 && frame_stride < row_stride * (size_t)height))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad strides or capacity");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    for (int attempt = 0;; ++attempt) {
+        PlanEntry* pe = nullptr;
+        int rc = get_plan(h, width, height, &pe);
+        if (rc != ORBX_OK) return rc;
+        const int group = std::min(h->prm.max_batch, n_frames);
+        rc = ensure_workspace(h, pe, group);
+        if (rc != ORBX_OK) return rc;
+        rc = set_kernel_attrs(h, pe);
+        if (rc != ORBX_OK) return rc;
+        // device-side output block for host outputs: [kps | desc | counts] per group
+        const size_t kp_bytes = (size_t)cap_per_frame * sizeof(OrbxKeyPoint), ds_bytes = (size_t)cap_per_frame * 32;
+        uint8_t *o_kps = nullptr, *o_desc = nullptr;
+        int32_t* o_counts = nullptr;
+        if (out_mem == ORBX_MEM_HOST) {
+            const size_t need = (kp_bytes + ds_bytes + 8) * (size_t)group + 256;
+            rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, need, false);
+            if (rc != ORBX_OK) return rc;
+            o_kps = (uint8_t*)h->d_out;
+            o_desc = o_kps + align_up((long long)kp_bytes * group, 64);
+            o_counts = (int32_t*)(o_desc + align_up((long long)ds_bytes * group, 64));
+        }
+        if (in_mem == ORBX_MEM_HOST) {
+            rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)width * height * group, false);
+            if (rc != ORBX_OK) return rc;
+        }
+        bool overflow = false;
+        for (int f0 = 0; f0 < n_frames; f0 += group) {
+            const int nf = std::min(group, n_frames - f0);
+            const uint8_t* d_imgs;
+            long long rs, fs;
+            if (in_mem == ORBX_MEM_HOST) {
+                if (row_stride == (size_t)width && (nf == 1 || frame_stride == (size_t)width * height)) {
+                    ORBX_CUDA(cudaMemcpyAsync(h->d_in, images + (size_t)f0 * frame_stride, (size_t)width * height * nf,
+                                              cudaMemcpyHostToDevice, st));
+                } else {
+                    for (int f = 0; f < nf; ++f)
+                        ORBX_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)f * width * height, (size_t)width,
+                                                    images + (size_t)(f0 + f) * frame_stride, row_stride, (size_t)width,
+                                                    (size_t)height, cudaMemcpyHostToDevice, st));
+                }
+                d_imgs = h->d_in; rs = width; fs = (long long)width * height;
+            } else {
+                d_imgs = images + (size_t)f0 * frame_stride; rs = (long long)row_stride; fs = (long long)frame_stride;
+            }
+            if (out_mem == ORBX_MEM_HOST) {
+                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps ? o_kps : nullptr, desc ? o_desc : nullptr,
+                                  cap_per_frame, o_counts, 0, STAGES_ALL);
+                if (rc != ORBX_OK) return rc;
+                if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, o_kps, kp_bytes * nf, cudaMemcpyDeviceToHost, st));
+                if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, o_desc, ds_bytes * nf, cudaMemcpyDeviceToHost, st));
+                if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, o_counts, 8 * (size_t)nf, cudaMemcpyDeviceToHost, st));
+                ORBX_CUDA(cudaStreamSynchronize(st));   // staging buffers are reused by the next group
+            } else {
+                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL);
+                if (rc != ORBX_OK) return rc;
+            }
+            // the workspace is reused by the next group: order the overflow check behind this group's kernels
+            ORBX_CUDA(cudaStreamSynchronize(st));
+            bool ov = false;
+            rc = check_overflow(h, nf, &ov);
+            if (rc != ORBX_OK) return rc;
+            if (ov) { overflow = true; break; }
+        }
+        if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
+        if (!overflow) return ORBX_OK;
+        // grow the candidate workspace and run again (results of a partial run are overwritten)
+        if (attempt >= 6) return fail(h, ORBX_ERR_CANDIDATE_OVERFLOW, "FAST candidate workspace overflow after regrowth");
+        h->cand_per_cell *= 4;
+        drop_plans(h);
+    }
+}
+
+int orbx_extract(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                 OrbxKeyPoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_out) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_out) *n_out = 0;
+    if (mono_out) *mono_out = 0;
+    int32_t cnt[2] = {0, 0};
+    int rc = orbx_extract_batch(h, image, ORBX_MEM_HOST, 1, width, height, stride, stride * (size_t)height, lap0, lap1, kps, desc,
+                                capacity, cnt, ORBX_MEM_HOST, nullptr);
+    if (rc != ORBX_OK) return rc;
+    if (n_out) *n_out = cnt[0];
+    if (mono_out) *mono_out = cnt[1];
+    if (cnt[0] > capacity && (kps || desc)) return fail(h, ORBX_ERR_CAPACITY, "keypoint capacity too small");
+    return ORBX_OK;
+}
+
+static int run_stages_single(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride, int stages) {
+    ORBX_CUDA(cudaSetDevice(h->device));
+    PlanEntry* pe = nullptr;
+    int rc;
+    if (stages & STAGES_PYRAMID) {
+        if (!image || width <= 0 || height <= 0) return fail(h, ORBX_ERR_EMPTY_IMAGE, "empty image");
+        rc = get_plan(h, width, height, &pe);
+        if (rc != ORBX_OK) return rc;
+        rc = ensure_workspace(h, pe, std::max(1, std::min(h->prm.max_batch, 1)));
+        if (rc != ORBX_OK) return rc;
+        rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)width * height, false);
+        if (rc != ORBX_OK) return rc;
+        ORBX_CUDA(cudaMemcpy2DAsync(h->d_in, (size_t)width, image, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        pe = h->cur;
+        if (!pe || h->resident_frames < 1) return fail(h, ORBX_ERR_NO_FRAME, "no resident pyramid");
+    }
+    rc = set_kernel_attrs(h, pe);
+    if (rc != ORBX_OK) return rc;
+    for (int attempt = 0;; ++attempt) {
+        rc = launch_group(h, pe, h->stream, h->d_in, width, (long long)width * height, 1, 0, 0, nullptr, nullptr, 0, nullptr, 0, stages);
+        if (rc != ORBX_OK) return rc;
+        ORBX_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
+        if (!(stages & STAGES_KEYPOINTS)) return ORBX_OK;
+        bool ov = false;
+        rc = check_overflow(h, 1, &ov);
+        if (rc != ORBX_OK) return rc;
+        if (!ov) return ORBX_OK;
+        (void)attempt;
+        return fail(h, ORBX_ERR_CANDIDATE_OVERFLOW, "FAST candidate workspace overflow (raise OrbxParams.cand_per_cell)");
+    }
+}
+
+int orbx_compute_pyramid(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    return run_stages_single(h, image, width, height, stride, STAGES_PYRAMID);
+}
+
+int orbx_compute_keypoints_octtree(OrbxHandle* h) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    return run_stages_single(h, nullptr, 0, 0, 0, STAGES_KEYPOINTS);
+}
+
+int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int min_x, int max_x, int min_y, int max_y,
+                            int n_features, OrbxKeyPoint* out, int capacity, int* n_out) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_out) *n_out = 0;
+    if (n < 0 || (n > 0 && !keys) || max_x <= min_x || max_y <= min_y || n_features < 0)
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad DistributeOctTree arguments");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int nIni = (int)roundf((float)(max_x - min_x) / (max_y - min_y));
+    if (nIni < 1) return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "aspect ratio < 0.5 (nIni == 0)");
+    const int CM = (1 << ORBX_COORD_BITS) - 1;
+    std::vector<uint2> cand((size_t)std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        const float x = keys[i].x, y = keys[i].y, r = keys[i].response;
+        if (!(x >= 0 && x <= CM && y >= 0 && y <= CM && x == floorf(x) && y == floorf(y) && r >= 0 && r <= 255 && r == floorf(r)))
+            return fail(h, ORBX_ERR_BAD_ARGUMENT, "DistributeOctTree keys must have integer coordinates in [0,4095] and integer responses in [0,255]");
+        cand[i] = make_uint2((uint32_t)x | ((uint32_t)y << ORBX_COORD_BITS) | ((uint32_t)r << 24), (uint32_t)i);
+    }
+    if (n >= (1 << 24)) return fail(h, ORBX_ERR_BAD_ARGUMENT, "too many keys");
+    // one-level plan + private workspace
+    OrbxPlan P;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = 1; P.lap0 = 0; P.lap1 = -1;
+    OrbxLevel& V = P.lv[0];
+    V.N = n_features; V.nIni = nIni; V.hX = (float)(max_x - min_x) / nIni; V.span_y = max_y - min_y;
+    V.cand_cap = std::max(n, 1); V.cand_off = 0;
+    V.kp_cap = std::max(n_features + 2, 4 * nIni) + 2; V.kp_off = 0; V.sf = 1.f;
+    P.kp_total = V.kp_cap; P.qt_nc = V.kp_cap + 2;
+    const size_t smem = (size_t)P.qt_nc * 64;
+    if (smem > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "n_features too large for the quadtree kernel");
+    OrbxWs w;
+    memset(&w, 0, sizeof(w));
+    int rc = ORBX_OK;
+    uint2* d_cand = nullptr; uint16_t* d_kn = nullptr; OrbxKpRec* d_rec = nullptr; int* d_cnt = nullptr; int2* d_lc = nullptr;
+    auto cleanup = [&]() { cudaFree(d_cand); cudaFree(d_kn); cudaFree(d_rec); cudaFree(d_cnt); cudaFree(d_lc); };
+#define ORBX_CUDA_L(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(h, ORBX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    ORBX_CUDA_L(cudaMalloc(&d_cand, cand.size() * sizeof(uint2)));
+    ORBX_CUDA_L(cudaMalloc(&d_kn, cand.size() * sizeof(uint16_t)));
+    ORBX_CUDA_L(cudaMalloc(&d_rec, (size_t)V.kp_cap * sizeof(OrbxKpRec)));
+    ORBX_CUDA_L(cudaMalloc(&d_cnt, sizeof(int)));
+    ORBX_CUDA_L(cudaMalloc(&d_lc, sizeof(int2)));
+    ORBX_CUDA_L(cudaMemcpyAsync(d_cand, cand.data(), cand.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA_L(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc;
+    w.cand_stride = (long long)cand.size(); w.kp_stride = V.kp_cap;
+    if (smem > 48 * 1024) ORBX_CUDA_L(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_octree<<<dim3(1, 1), ORBX_QT_THREADS, smem, h->stream>>>(P, w);
+    h->total_launches += 1; h->stage_launches += 1;
+    ORBX_CUDA_L(cudaGetLastError());
+    int2 lc;
+    ORBX_CUDA_L(cudaMemcpyAsync(&lc, d_lc, sizeof(int2), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA_L(cudaStreamSynchronize(h->stream));
+    std::vector<OrbxKpRec> rec((size_t)std::max(lc.x, 1));
+    ORBX_CUDA_L(cudaMemcpy(rec.data(), d_rec, (size_t)lc.x * sizeof(OrbxKpRec), cudaMemcpyDeviceToHost));
+#undef ORBX_CUDA_L
+    cleanup();
+    if (n_out) *n_out = lc.x;
+    for (int i = 0; i < lc.x && i < capacity; ++i) out[i] = keys[rec[i].src];
+    if (lc.x > capacity) rc = fail(h, ORBX_ERR_CAPACITY, "keypoint capacity too small");
+    return rc;
+}
+
+int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height) {
+    if (!h || !h->cur) return ORBX_ERR_NO_FRAME;
+    if (level < 0 || level >= h->cur->plan.nlevels) return ORBX_ERR_BAD_ARGUMENT;
+    if (width) *width = h->cur->plan.lv[level].w;
+    if (height) *height = h->cur->plan.lv[level].h;
+    return ORBX_OK;
+}
+
+static int check_frame(OrbxHandle* h, int frame, int level) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (!h->cur || frame < 0 || frame >= h->resident_frames) return fail(h, ORBX_ERR_NO_FRAME, "frame not resident");
+    if (level < 0 || level >= h->cur->plan.nlevels) return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad level");
+    return ORBX_OK;
+}
+
+int orbx_get_pyramid_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride, int with_border) {
+    int rc = check_frame(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    if (!dst) return fail(h, ORBX_ERR_BAD_ARGUMENT, "null destination");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const OrbxLevel& V = h->cur->plan.lv[level];
+    const int b = with_border ? ORBX_EDGE : 0;
+    const uint8_t* src = h->ws.pyr + (size_t)frame * h->ws.pyr_stride + V.plane_off + (size_t)(ORBX_EDGE - b) * V.pitch + (ORBX_PADL - b);
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(cudaMemcpy2D(dst, dst_stride, src, (size_t)V.pitch, (size_t)V.w + 2 * b, (size_t)V.h + 2 * b, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_get_blurred_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    int rc = check_frame(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    if (!dst) return fail(h, ORBX_ERR_BAD_ARGUMENT, "null destination");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const OrbxLevel& V = h->cur->plan.lv[level];
+    const uint8_t* src = h->ws.blur + (size_t)frame * h->ws.blur_stride + V.blur_off;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(cudaMemcpy2D(dst, dst_stride, src, (size_t)V.blur_pitch, (size_t)V.w, (size_t)V.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* kps, int capacity, int* n_out) {
+    int rc = check_frame(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const OrbxPlan& P = h->cur->plan;
+    const OrbxLevel& V = P.lv[level];
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    int2 lc;
+    ORBX_CUDA(cudaMemcpy(&lc, h->ws.level_count + (size_t)frame * P.nlevels + level, sizeof(int2), cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = lc.x;
+    const int n = std::min(lc.x, capacity);
+    if (n > 0 && kps) {
+        std::vector<OrbxKpRec> rec((size_t)n);
+        ORBX_CUDA(cudaMemcpy(rec.data(), h->ws.kprec + (size_t)frame * h->ws.kp_stride + V.kp_off, (size_t)n * sizeof(OrbxKpRec), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) {
+            kps[i].x = rec[i].x; kps[i].y = rec[i].y; kps[i].size = V.kp_size; kps[i].angle = rec[i].angle;
+            kps[i].response = rec[i].response; kps[i].octave = level; kps[i].class_id = -1;
+        }
+    }
+    return ORBX_OK;
+}
+
+int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores, uint32_t* order,
+                              int capacity, int* n_out) {
+    int rc = check_frame(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const OrbxPlan& P = h->cur->plan;
+    const OrbxLevel& V = P.lv[level];
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    ORBX_CUDA(cudaMemcpy(&cnt, h->ws.cand_count + (size_t)frame * P.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, V.cand_cap);
+    if (n_out) *n_out = cnt;
+    const int n = std::min(cnt, capacity);
+    if (n > 0) {
+        std::vector<uint2> c((size_t)n);
+        ORBX_CUDA(cudaMemcpy(c.data(), h->ws.cand + (size_t)frame * h->ws.cand_stride + V.cand_off, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+        const uint32_t CM = (1u << ORBX_COORD_BITS) - 1;
+        for (int i = 0; i < n; ++i) {
+            if (xs) xs[i] = (int32_t)(c[i].x & CM);
+            if (ys) ys[i] = (int32_t)((c[i].x >> ORBX_COORD_BITS) & CM);
+            if (scores) scores[i] = (int32_t)(c[i].x >> 24);
+            if (order) order[i] = c[i].y;
+        }
+    }
+    return ORBX_OK;
+}
+
+int orbx_stage_times(OrbxHandle* h, float* ms, int64_t* launches) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    for (int s = 0; s < ORBX_NUM_STAGES; ++s) { if (ms) ms[s] = (float)h->stage_ms[s]; h->stage_ms[s] = 0; }
+    if (launches) *launches = h->stage_launches;
+    h->stage_launches = 0;
+    return ORBX_OK;
+}
+
+int64_t orbx_launch_count(const OrbxHandle* h) { return h ? h->total_launches : 0; }
+
+int orbx_synchronize(OrbxHandle* h) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+void* orbx_get_stream(const OrbxHandle* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// extractorb_b200/csrc/orbx_plan.h -- geometry ("plan") and workspace descriptors shared by host and device.
+//
+// A Plan is everything that depends only on (image size, constructor arguments): level sizes, plane
+// layout in HBM, resize tables, the FAST cell grid and the quadtree quotas.  It is built once on the
+// host (orbx_api.cu: build_plan) and passed to every kernel by value as a __grid_constant__ parameter.
+#ifndef ORBX_PLAN_H_
+#define ORBX_PLAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE 19          // EDGE_THRESHOLD, reference ORBextractor.cc:72
+#define ORBX_PADL 32          // byte column of ROI x=0 inside a plane row (>= 19, 32-byte aligned rows)
+#define ORBX_HALF_PATCH 15    // HALF_PATCH_SIZE, :71
+#define ORBX_FAST_BORDER 16   // EDGE_THRESHOLD-3, :781
+#define ORBX_COORD_BITS 12    // candidate x/y packing: x | y<<12 | score<<24
+#define ORBX_MAX_LEVEL_DIM (4095 + 2 * ORBX_FAST_BORDER)
+#define ORBX_ORD_CELL_SHIFT 14  // emission-order key: cellseq<<14 | ycell<<7 | xcell
+#define ORBX_MAX_CELL_DIM 127
+
+struct OrbxLevel {
+    int w, h;              // level (ROI) size, reference ORBextractor.cc:1171
+    int pitch;             // plane row pitch in bytes (multiple of 64)
+    int plane_rows;        // h + 38
+    long long plane_off;   // byte offset of the plane (its top border row) inside a frame's pyramid block
+    int blur_pitch;        // blurred plane row pitch (multiple of 16), no border
+    long long blur_off;    // byte offset inside a frame's blur block
+    int xtab_off, ytab_off;  // offsets into the resize tables (entries), level >= 1
+    // FAST cell grid, reference :781-814
+    int nCols, nRows, wCell, hCell;
+    int cell_off, ncells;  // slice of the cell table
+    // quadtree, reference :548-568
+    int N;                 // mnFeaturesPerLevel[level]
+    int nIni;
+    float hX;
+    int span_y;            // maxY - minY
+    int cand_cap;          // candidate capacity (entries)
+    long long cand_off;    // entry offset inside a frame's candidate block
+    int kp_cap;            // kept-keypoint capacity: max(N + 2, 4 * nIni) + slack
+    int kp_off;            // record offset inside a frame's keypoint staging block
+    float sf;              // mvScaleFactor[level]
+    float kp_size;         // (float)(int)(31 * sf), :872
+};
+
+struct OrbxPlan {
+    int nlevels;
+    int width, height;
+    int ini_th, min_th;
+    int ncells_total;
+    int kp_total;          // sum of kp_cap
+    int qt_nc;             // node capacity of the quadtree kernel (max over levels)
+    int fast_tp;           // FAST smem tile pitch (bytes)
+    int fast_trows;        // FAST smem tile rows
+    int fast_qcap;         // FAST smem queue capacity (entries)
+    int lap0, lap1;
+    int umax[ORBX_HALF_PATCH + 1];
+    OrbxLevel lv[ORBX_MAX_LEVELS];
+};
+
+// One FAST cell (reference ORBextractor.cc:797-814): the cell image is [x0, x0+cw) x [y0, y0+ch) in
+// level coordinates, FAST evaluates its pixels >= 3 px inside; xoff/yoff = (j*wCell, i*hCell).
+struct OrbxCell {
+    uint16_t x0, y0;
+    uint8_t cw, ch;
+    uint8_t level, pad;
+    uint32_t ordbase;      // (i * nCols + j) << ORBX_ORD_CELL_SHIFT
+    uint16_t xoff, yoff;
+};
+
+// Kept keypoint record written by the quadtree kernel, completed by the describe kernel.
+struct OrbxKpRec {
+    float x, y;            // level coordinates (ROI), +16 border already added (:875-876)
+    float response;
+    float angle;
+    int lap_before;        // lapping keypoints earlier in this level's list
+    int src;               // index of the winning candidate
+};
+
+// Device workspace for one launch group of up to `frames` frames.
+struct OrbxWs {
+    uint8_t* pyr;          long long pyr_stride;    // per-frame byte strides
+    uint8_t* blur;         long long blur_stride;
+    uint2* cand;           long long cand_stride;   // entries
+    uint16_t* keynode;                                // same indexing as cand
+    OrbxKpRec* kprec;      int kp_stride;             // records
+    int* cand_count;       // [frame][level]
+    int2* level_count;     // [frame][level] = {n, n_lapping}
+    int* flags;            // [frame] bit0: candidate overflow
+    const int2* xtab;      // resize: {src offset, a0 | a1<<16}
+    const int2* ytab;
+    const OrbxCell* cells;
+    const int8_t* pattern; // 256 x 4 int8
+};
+
+#endif

@@ -1,0 +1,146 @@
+/*
+ * include/orbx.h -- C-ABI of libextractorb_cuda.so (sm_100a CUDA kernels behind plain pointers).
+ *
+ * This is the drop-in boundary for the ONE hot path this project accelerates: the path
+ * Frame::ExtractORB (reference src/Frame.cc:419-427) drives through ORBextractor::operator()
+ * (reference src/orb_extractor/ORBextractor.cc:1078-1162, 5-argument twin ORBExtractor.cpp:980-1112).
+ * The C++ class in include/ORBextractor.h only unwraps cv::InputArray/OutputArray and forwards here.
+ * There is NO CPU fallback: every entry point fails with an error code when CUDA is unavailable.
+ *
+ * Conventions: every function returns ORBX_OK (0) or a negative OrbxStatus; nothing throws, aborts or
+ * writes to stdout.  A handle owns one CUDA stream + workspace on one device and is NOT re-entrant
+ * (like a reference ORBextractor instance, which mutates mvImagePyramid); distinct handles may be used
+ * concurrently from different host threads (stereo left/right, reference src/Frame.cc:109-112).
+ */
+#ifndef ORBX_H_
+#define ORBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ORBX_API __attribute__((visibility("default")))
+#else
+#define ORBX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum OrbxStatus {
+    ORBX_OK = 0,
+    ORBX_ERR_EMPTY_IMAGE = -1,        /* reference returns -1 for an empty image (ORBextractor.cc:1083) */
+    ORBX_ERR_BAD_ARGUMENT = -2,
+    ORBX_ERR_LEVEL_TOO_SMALL = -3,    /* a pyramid level has no 30-px cell / aspect < 0.5: UB in the reference */
+    ORBX_ERR_IMAGE_TOO_LARGE = -4,    /* a level is wider/taller than 4127 px */
+    ORBX_ERR_CUDA = -5,               /* see orbx_last_error() */
+    ORBX_ERR_CAPACITY = -6,           /* caller's keypoint capacity too small; *n_out holds the need */
+    ORBX_ERR_CANDIDATE_OVERFLOW = -7, /* more FAST candidates than the workspace holds even after regrowth */
+    ORBX_ERR_NO_FRAME = -8,           /* accessor called before any extraction / frame index not resident */
+    ORBX_ERR_NO_DEVICE = -9
+} OrbxStatus;
+
+/* Constructor arguments of ORBextractor (reference ORBextractor.cc:408-411) + build-side knobs. */
+typedef struct OrbxParams {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t cell_size;     /* W of ComputeKeyPointsOctTree; 0 -> 30 (reference ORBextractor.cc:777) */
+    int32_t max_batch;     /* frames processed per internal launch group; 0 -> 1 */
+    int32_t cand_per_cell; /* initial FAST-candidate capacity per grid cell; 0 -> 64 (grows on overflow) */
+    int32_t flags;         /* ORBX_FLAG_* */
+} OrbxParams;
+
+#define ORBX_FLAG_PROFILE 1 /* record CUDA-event time per stage (orbx_stage_times) */
+
+/* Same 28-byte layout as cv::KeyPoint. */
+typedef struct OrbxKeyPoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} OrbxKeyPoint;
+
+typedef struct OrbxHandle OrbxHandle;
+
+enum { ORBX_MEM_HOST = 0, ORBX_MEM_DEVICE = 1 };
+
+/* Pipeline stages, in launch order (index into orbx_stage_times output). */
+enum {
+    ORBX_STAGE_PYRAMID = 0, /* ComputePyramid            ORBextractor.cc:1164-1219 */
+    ORBX_STAGE_FAST = 1,    /* cell loop + cv::FAST      ORBextractor.cc:797-864   */
+    ORBX_STAGE_OCTREE = 2,  /* DistributeOctTree         ORBextractor.cc:544-771   */
+    ORBX_STAGE_BLUR = 3,    /* GaussianBlur 7x7          ORBextractor.cc:1126-1127 */
+    ORBX_STAGE_DESCRIBE = 4,/* IC_Angle + rBRIEF + scatter  :75-145, :1131-1159     */
+    ORBX_NUM_STAGES = 5
+};
+
+ORBX_API const char* orbx_status_string(int status);
+ORBX_API const char* orbx_last_error(const OrbxHandle* h);
+
+/* ORBextractor::ORBextractor (ORBextractor.cc:408-475). */
+ORBX_API int orbx_create(const OrbxParams* params, int device, OrbxHandle** out);
+ORBX_API void orbx_destroy(OrbxHandle* h);
+
+/* Constructor tables: mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2 (nlevels floats
+ * each), mnFeaturesPerLevel (nlevels ints), umax (16 ints).  Any pointer may be NULL. */
+ORBX_API int orbx_get_tables(const OrbxHandle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* features_per_level, int32_t* umax16);
+/* Upper bound of keypoints one frame can yield (sum over levels of max(N_l + 2, 4 * nIni)). */
+ORBX_API int orbx_max_keypoints(const OrbxHandle* h, int width, int height);
+
+/* ORBextractor::operator() (ORBextractor.cc:1078-1162) on one host image (CV_8UC1, `stride` bytes per
+ * row).  kps/desc receive the keypoints and 32-byte descriptors in the reference's two-ended order
+ * (lapping keypoints filled from the back); *n_out = total, *mono_out = the reference's return value. */
+ORBX_API int orbx_extract(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride,
+                 int lap0, int lap1, OrbxKeyPoint* kps, uint8_t* desc, int capacity,
+                 int* n_out, int* mono_out);
+
+/* The same path over n_frames independent frames (the data-parallel form: one launch group per
+ * max_batch frames).  images/kps/desc/counts live in `in_mem`/`out_mem` memory (ORBX_MEM_*); frame f's
+ * outputs start at kps + f*cap_per_frame, desc + f*cap_per_frame*32, counts + 2*f ({n, mono}).
+ * `stream` is a cudaStream_t (NULL -> the handle's own stream).  With device outputs the call is
+ * asynchronous on that stream; with any host buffer it returns after the results have landed. */
+ORBX_API int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height,
+                       size_t row_stride, size_t frame_stride, int lap0, int lap1,
+                       OrbxKeyPoint* kps, uint8_t* desc, int cap_per_frame, int32_t* counts, int out_mem,
+                       void* stream);
+
+/* Stage-wise entry points mirroring the reference's public methods (inc/ORBextractor.h:89-92), which the
+ * demos call directly (src/orb_extractor/main_orb_extractor.cpp:44-46). */
+ORBX_API int orbx_compute_pyramid(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride);
+ORBX_API int orbx_compute_keypoints_octtree(OrbxHandle* h); /* on the resident pyramid; results via orbx_get_level_keypoints */
+/* ORBextractor::DistributeOctTree (ORBextractor.cc:544-771) on caller-supplied keypoints (host).
+ * Ties on response keep the earlier input keypoint; equal-size nodes split later-created first. */
+ORBX_API int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int min_x, int max_x, int min_y,
+                            int max_y, int n_features, OrbxKeyPoint* out, int capacity, int* n_out);
+
+/* State of the most recent extraction.  `frame` indexes the frames of the last launch group
+ * (0 for orbx_extract). */
+ORBX_API int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height);
+/* mvImagePyramid[level] (inc/ORBextractor.h:85): with_border=0 copies the w x h level, 1 the
+ * (w+38) x (h+38) plane including the 19-px reflect-101 border. */
+ORBX_API int orbx_get_pyramid_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride, int with_border);
+/* allKeypoints[level] in level coordinates with angle set (== allLevelsKeypoints, ORBextractor.cc:1094). */
+ORBX_API int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* kps, int capacity, int* n_out);
+/* FAST candidates of the cell loop (ORBextractor.cc:855-860): x, y relative to (16,16), score, and the
+ * emission-order key (cell row, cell col, y, x).  Storage order is unspecified; sort by `order`. */
+ORBX_API int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores,
+                              uint32_t* order, int capacity, int* n_out);
+/* The 7x7 sigma-2 blurred level the descriptors were sampled from (ORBextractor.cc:1126-1127). */
+ORBX_API int orbx_get_blurred_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* Sum of CUDA-event milliseconds per stage and number of kernel launches since the last call
+ * (requires ORBX_FLAG_PROFILE; resets the accumulators). */
+ORBX_API int orbx_stage_times(OrbxHandle* h, float* ms_per_stage, int64_t* launches);
+/* Total kernel launches issued by this handle since creation. */
+ORBX_API int64_t orbx_launch_count(const OrbxHandle* h);
+ORBX_API int orbx_synchronize(OrbxHandle* h);
+/* The handle's cudaStream_t (for callers that time with their own events). */
+ORBX_API void* orbx_get_stream(const OrbxHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H_ */

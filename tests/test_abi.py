@@ -1,0 +1,74 @@
+"""CPU-side checks of the C-ABI boundary: the shared library loads, exports every symbol that
+include/orbx.h declares, and refuses to work without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from extractorb_b200 import build
+    build.build_cuda()
+    import extractorb_b200 as ex
+    return ex.load_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    return sorted(set(re.findall(r"ORBX_API[^;(]*?\b(orbx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("orbx_create", "orbx_destroy", "orbx_extract", "orbx_extract_batch", "orbx_get_pyramid_level",
+                 "orbx_get_level_keypoints", "orbx_get_tables", "orbx_distribute_octtree", "orbx_compute_pyramid",
+                 "orbx_compute_keypoints_octtree"):
+        assert must in syms
+    assert len(syms) >= 20
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert getattr(lib, name) is not None, name
+
+
+def test_status_strings(lib):
+    assert lib.orbx_status_string(0) == b"ok"
+    assert lib.orbx_status_string(-1) == b"empty image"
+    assert b"unknown" in lib.orbx_status_string(-1234)
+
+
+def test_bad_arguments_rejected_before_touching_cuda(lib):
+    import extractorb_b200 as ex
+    h = C.c_void_p()
+    assert lib.orbx_create(None, 0, C.byref(h)) == -2
+    bad = ex.OrbxParams(1000, 1.0, 8, 20, 7, 0, 0, 0, 0)       # scaleFactor must be > 1
+    assert lib.orbx_create(C.byref(bad), 0, C.byref(h)) == -2
+    bad = ex.OrbxParams(1000, 1.2, 0, 20, 7, 0, 0, 0, 0)       # nlevels >= 1
+    assert lib.orbx_create(C.byref(bad), 0, C.byref(h)) == -2
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device construction must fail loudly; with one it must succeed."""
+    import torch
+    import extractorb_b200 as ex
+    if torch.cuda.is_available():
+        e = ex.ORBextractor(1000, 1.2, 8, 20, 7)
+        e.close()
+    else:
+        with pytest.raises(ex.OrbxError) as ei:
+            ex.ORBextractor(1000, 1.2, 8, 20, 7)
+        assert ei.value.code in (-9, -5)
+
+
+def test_python_mirror_matches_reference_class_surface():
+    """Names of ORB_SLAM3::ORBextractor (reference inc/ORBextractor.h:44-111) exist on the Python mirror."""
+    import extractorb_b200 as ex
+    for name in ("GetLevels", "GetScaleFactor", "GetScaleFactors", "GetInverseScaleFactors", "GetScaleSigmaSquares",
+                 "GetInverseScaleSigmaSquares", "ComputePyramid", "ComputeKeyPointsOctTree", "DistributeOctTree",
+                 "mvImagePyramid", "HARRIS_SCORE", "FAST_SCORE", "__call__"):
+        assert hasattr(ex.ORBextractor, name), name
