@@ -369,9 +369,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
         ORBX_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)nf * sizeof(int), st));
-        const long long warps = (long long)P.ncells_total * nf;
-        const unsigned blocks = (unsigned)((warps + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS);
-        k_fast_cells<<<blocks, ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, nf);
+        k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
         k_octree<<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);

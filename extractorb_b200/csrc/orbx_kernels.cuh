@@ -126,14 +126,35 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ t, int p, i
     return max(bright, -dark);
 }
 
+// Upper bound of best(p) from the 8 antipodal ring pairs: every arc of 9 contiguous ring pixels contains
+// at least one pixel of each pair, so  best <= max( c - max_pairs(min(a,b)),  min_pairs(max(a,b)) - c ).
+// The first two pairs (vertical, horizontal) reject most pixels of smooth regions after 5 loads.
+__device__ __forceinline__ bool fast_quick(const uint8_t* __restrict__ t, int p, int tp, int th) {
+    const int c = t[p];
+    const int a0 = t[p + 3 * tp], a8 = t[p - 3 * tp], a4 = t[p + 3], a12 = t[p - 3];
+    int dk = max(min(a0, a8), min(a4, a12));   // dark side:   need c - dk > th
+    int br = min(max(a0, a8), max(a4, a12));   // bright side: need br - c > th
+    if (c - dk <= th && br - c <= th) return false;
+    const int a2 = t[p + 2 * tp + 2], a10 = t[p - 2 * tp - 2], a6 = t[p - 2 * tp + 2], a14 = t[p + 2 * tp - 2];
+    dk = __vimax3_s32(dk, min(a2, a10), min(a6, a14));
+    br = __vimin3_s32(br, max(a2, a10), max(a6, a14));
+    if (c - dk <= th && br - c <= th) return false;
+    const int a1 = t[p + 3 * tp + 1], a9 = t[p - 3 * tp - 1], a3 = t[p + tp + 3], a11 = t[p - tp - 3];
+    const int a5 = t[p - tp + 3], a13 = t[p + tp - 3], a7 = t[p - 3 * tp + 1], a15 = t[p + 3 * tp - 1];
+    dk = __vimax3_s32(dk, min(a1, a9), min(a3, a11));
+    br = __vimin3_s32(br, max(a1, a9), max(a3, a11));
+    dk = __vimax3_s32(dk, min(a5, a13), min(a7, a15));
+    br = __vimin3_s32(br, max(a5, a13), max(a7, a15));
+    return c - dk > th || br - c > th;
+}
+
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32)
-k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int nframes) {
+k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     extern __shared__ __align__(16) uint8_t smem_fast[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * ORBX_FAST_WARPS + wib;
-    const int frame = (int)(gw / plan.ncells_total);
-    if (frame >= nframes) return;
-    const int ci = (int)(gw - (long long)frame * plan.ncells_total);
+    const int ci = blockIdx.x * ORBX_FAST_WARPS + wib;
+    const int frame = blockIdx.y;
+    if (ci >= plan.ncells_total) return;
     const OrbxCell cell = ws.cells[ci];
     const OrbxLevel& L = plan.lv[cell.level];
 
@@ -151,15 +172,14 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int nframes
     const int nwords = (a + cw + 3) >> 2;
     const uint8_t* g0 = plane + (long long)(ORBX_EDGE + cell.y0) * L.pitch + (gx - a);
     {
-        const int rows_per_it = 32 / nwords;  // nwords <= 33 -> at least... guarded below
+        const int rows_per_it = 32 / nwords;
         if (rows_per_it >= 1) {
             const int lr = lane / nwords, lw = lane - lr * nwords;
-            for (int r = lr; r < ch; r += rows_per_it) {
-                if (lr < rows_per_it) {
+            if (lr < rows_per_it)
+                for (int r = lr; r < ch; r += rows_per_it) {
                     const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(g0 + (long long)r * L.pitch) + lw);
                     *reinterpret_cast<uint32_t*>(tile + r * tp + 4 * lw) = v;
                 }
-            }
         } else {
             for (int r = 0; r < ch; ++r)
                 for (int wd = lane; wd < nwords; wd += 32) {
@@ -171,83 +191,59 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int nframes
     for (int i = lane; i < (tile_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
     __syncwarp();
 
-    // ---- quick rejection over the interior, compaction of the survivors into `queue` ----
     const int iw = cw - 6, ih = ch - 6;
     const int npix = iw * ih;
-    const unsigned magic = (1u << 24) / (unsigned)iw + 1u;  // idx / iw == (idx * magic) >> 24 for idx < 4096*4
-    const int tlow = min(plan.ini_th, plan.min_th);
-    int qn = 0;
-    for (int base = 0; base < npix; base += 32) {
-        const int idx = base + lane;
-        bool pass = false;
-        int p = 0;
-        if (idx < npix) {
-            const int r = (int)(((unsigned)idx * magic) >> 24);
-            const int c = idx - r * iw;
-            p = (r + 3) * tp + a + c + 3;
-            const int v = tile[p];
-            const int lo = v - tlow, hi = v + tlow;
-#define ORBX_CLS(q) ((int)(tile[q] < lo) | ((int)(tile[q] > hi) << 1))
-            int m = ORBX_CLS(p + 3 * tp) | ORBX_CLS(p - 3 * tp);
-            if (m) {
-                m &= ORBX_CLS(p + 3) | ORBX_CLS(p - 3);
-                if (m) {
-                    m &= ORBX_CLS(p + 2 * tp + 2) | ORBX_CLS(p - 2 * tp - 2);
-                    m &= ORBX_CLS(p - 2 * tp + 2) | ORBX_CLS(p + 2 * tp - 2);
-                    if (m) {
-                        m &= ORBX_CLS(p + 3 * tp + 1) | ORBX_CLS(p - 3 * tp - 1);
-                        m &= ORBX_CLS(p + tp + 3) | ORBX_CLS(p - tp - 3);
-                        m &= ORBX_CLS(p - tp + 3) | ORBX_CLS(p + tp - 3);
-                        m &= ORBX_CLS(p - 3 * tp + 1) | ORBX_CLS(p + 3 * tp - 1);
-                        pass = m != 0;
-                    }
+    const unsigned magic = (1u << 24) / (unsigned)iw + 1u;  // idx / iw == (idx * magic) >> 24 (idx < 2^14, iw < 2^7)
+    // The reference detects at iniThFAST and re-runs the cell at minThFAST only if that found nothing
+    // (:818-838); the same two phases here, the second one skipped when it cannot add anything.
+    int qn = 0, n_out = 0, use_th = plan.ini_th;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1) {
+            if (plan.min_th >= plan.ini_th) break;
+            use_th = plan.min_th;
+        }
+        // ---- quick rejection over the interior, survivors compacted into `queue` ----
+        qn = 0;
+        for (int base = 0; base < npix; base += 32) {
+            const int idx = base + lane;
+            bool pass = false;
+            int p = 0;
+            if (idx < npix) {
+                const int r = (int)(((unsigned)idx * magic) >> 24);
+                p = (r + 3) * tp + a + (idx - r * iw) + 3;
+                pass = fast_quick(tile, p, tp, use_th);
+            }
+            const unsigned bal = __ballot_sync(ORBX_FULL_MASK, pass);
+            if (pass) queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
+            qn += __popc(bal);
+        }
+        __syncwarp();
+        // ---- exact corner measure for the queued pixels ----
+        for (int e = lane; e < qn; e += 32) {
+            const int p = queue[e];
+            const int best = fast_best(tile, p, tp);
+            if (best > use_th) score[p] = (uint8_t)best;
+            else queue[e] = 0xffff;
+        }
+        __syncwarp();
+        // ---- strict 3x3 non-max suppression (pixels at or below the threshold count as 0, like cv::FAST) ----
+        n_out = 0;
+        for (int base = 0; base < qn; base += 32) {
+            const int e = base + lane;
+            bool lm = false;
+            if (e < qn) {
+                const int p = queue[e];
+                if (p != 0xffff) {
+                    const int s = score[p];
+                    lm = s > score[p - 1] && s > score[p + 1] && s > score[p - tp - 1] && s > score[p - tp] &&
+                         s > score[p - tp + 1] && s > score[p + tp - 1] && s > score[p + tp] && s > score[p + tp + 1];
+                    if (!lm) queue[e] = 0xffff;
                 }
             }
-#undef ORBX_CLS
+            n_out += __popc(__ballot_sync(ORBX_FULL_MASK, lm));
         }
-        const unsigned bal = __ballot_sync(ORBX_FULL_MASK, pass);
-        if (pass) queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
-        qn += __popc(bal);
-    }
-    __syncwarp();
-
-    // ---- exact corner measure for the queued pixels ----
-    for (int e = lane; e < qn; e += 32) {
-        const int p = queue[e];
-        const int best = fast_best(tile, p, tp);
-        if (best > tlow) score[p] = (uint8_t)best;
-        else queue[e] = 0xffff;
-    }
-    __syncwarp();
-
-    // ---- strict 3x3 non-max suppression + per-cell threshold choice ----
-    int n_ini = 0;
-    for (int base = 0; base < qn; base += 32) {
-        const int e = base + lane;
-        bool is_ini = false;
-        if (e < qn) {
-            const int p = queue[e];
-            bool lm = false;
-            if (p != 0xffff) {
-                const int s = score[p];
-                lm = s > score[p - 1] && s > score[p + 1] && s > score[p - tp - 1] && s > score[p - tp] &&
-                     s > score[p - tp + 1] && s > score[p + tp - 1] && s > score[p + tp] && s > score[p + tp + 1];
-                is_ini = lm && s > plan.ini_th;
-            }
-            if (!lm) queue[e] = 0xffff;
-        }
-        n_ini += __popc(__ballot_sync(ORBX_FULL_MASK, is_ini));
-    }
-    const int use_th = n_ini > 0 ? plan.ini_th : plan.min_th;
-    int n_out = 0;
-    for (int base = 0; base < qn; base += 32) {
-        const int e = base + lane;
-        bool keep = false;
-        if (e < qn) {
-            const int p = queue[e];
-            keep = p != 0xffff && (int)score[p] > use_th;
-        }
-        n_out += __popc(__ballot_sync(ORBX_FULL_MASK, keep));
+        if (n_out > 0) break;
+        __syncwarp();
     }
     if (n_out == 0) return;
 
@@ -260,20 +256,17 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int nframes
         if (lane == 0) atomicOr(ws.flags + frame, 1);
     }
     uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
+    const unsigned tpmagic = (1u << 24) / (unsigned)tp + 1u;  // p / tp (p < 2^14, tp <= 136)
     int written = 0;
     for (int base = 0; base < qn; base += 32) {
         const int e = base + lane;
-        bool keep = false;
-        int p = 0;
-        if (e < qn) {
-            p = queue[e];
-            keep = p != 0xffff && (int)score[p] > use_th;
-        }
+        const int p = e < qn ? queue[e] : 0xffff;
+        const bool keep = p != 0xffff;
         const unsigned bal = __ballot_sync(ORBX_FULL_MASK, keep);
         if (keep) {
             const int slot = slot0 + written + __popc(bal & ((1u << lane) - 1u));
             if (slot < L.cand_cap) {
-                const int r = p / tp;
+                const int r = (int)(((unsigned)p * tpmagic) >> 24);
                 const int c = p - r * tp - a;  // cell-image coordinates (>= 3)
                 const uint32_t x = (uint32_t)(c + cell.xoff), y = (uint32_t)(r + cell.yoff);
                 const uint32_t resp = (uint32_t)score[p] - 1u;
