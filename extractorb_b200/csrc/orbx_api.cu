@@ -41,6 +41,9 @@ struct PlanEntry {
     size_t fast_smem = 0, qt_smem = 0;
     int max_cells_dim = 0;
     int blur_tiles = 0;
+    int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
+    int rs_pitch[ORBX_MAX_LEVELS] = {0};
+    int border_items = 0;                   // max over levels >= 1 of the border kernel's work items
 };
 
 struct StageEvents { cudaEvent_t ev[ORBX_NUM_STAGES + 1]; };
@@ -199,6 +202,20 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 linear_axis_table(S.w, V.w, pe->xtab);
                 linear_axis_table(S.h, V.h, pe->ytab);
             }
+            // shared-memory window of the resize kernel: exact maxima over its 128x16 tiles
+            int rows = 1, cols = 1;
+            for (int y0 = 0; y0 < V.h; y0 += ORBX_RS_TH) {
+                const int yl = std::min(y0 + ORBX_RS_TH, V.h) - 1;
+                rows = std::max(rows, std::min(pe->ytab[V.ytab_off + yl].x + 1, S.h - 1) - pe->ytab[V.ytab_off + y0].x + 1);
+            }
+            for (int x0 = 0; x0 < V.w; x0 += ORBX_RS_TW) {
+                const int xl = std::min(x0 + ORBX_RS_TW, V.w) - 1;
+                cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
+            }
+            pe->rs_rows[l] = rows;
+            pe->rs_pitch[l] = (int)align_up(cols + 3 + 3, 4);
+            const int pw = V.pitch / 4, rw0 = (ORBX_PADL + V.w) / 4;
+            pe->border_items = std::max(pe->border_items, 2 * ORBX_EDGE * pw + V.h * (ORBX_PADL / 4 + pw - rw0));
         }
         // FAST cell grid, :781-814
         const int minBX = ORBX_FAST_BORDER, minBY = ORBX_FAST_BORDER;
@@ -360,8 +377,13 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const OrbxLevel& V = P.lv[l];
-            const dim3 grd((V.pitch / 4 + 63) / 64, (V.plane_rows + 3) / 4, nf);
-            k_pyr_resize<<<grd, blk, 0, st>>>(P, ws, l);
+            const dim3 grd((V.w + ORBX_RS_TW - 1) / ORBX_RS_TW, (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nf);
+            const size_t smem = align_up((long long)pe->rs_rows[l] * pe->rs_pitch[l], 16) + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2;
+            k_pyr_resize<<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
+            ++launches;
+        }
+        if (P.nlevels > 1) {
+            k_pyr_border<<<dim3((pe->border_items + 255) / 256, P.nlevels - 1, nf), 256, 0, st>>>(P, ws);
             ++launches;
         }
     }
@@ -419,6 +441,12 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
         ORBX_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->fast_smem));
     if (pe->qt_smem > 48 * 1024)
         ORBX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+    size_t rs = 0;
+    for (int l = 1; l < pe->plan.nlevels; ++l)
+        rs = std::max(rs, (size_t)align_up((long long)pe->rs_rows[l] * pe->rs_pitch[l], 16) + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2);
+    if (rs > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "scale factor too large for the resize kernel's shared memory");
+    if (rs > 48 * 1024)
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     return ORBX_OK;
 }
 

@@ -52,43 +52,133 @@ k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8
     *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch + wx * 4) = word;
 }
 
-// cv::resize INTER_LINEAR, 8UC1 fixed point (11-bit coefficients): see oracle/cv_prims.c for the model.
+// cv::resize INTER_LINEAR, 8UC1 fixed point (11-bit coefficients), the model pinned in oracle/cv_prims.c:
+//   H(y', x) = S[y'][sx]*a0 + S[y'][sx+1]*a1                      (int32, coefficients x2048)
+//   dst(y,x) = ( ((b0*(H(sy,x)>>4))>>16) + ((b1*(H(sy+1,x)>>4))>>16) + 2 ) >> 2
+// Separable and staged through shared memory: a CTA owns a 128x16 tile of the level (ROI only), stages
+// the source rows/columns it needs with aligned 32-bit loads, runs the horizontal pass once per staged
+// source row (H>>4 fits 16 bits) and the vertical pass from shared memory, and stores aligned words.
+// Borders are filled afterwards by k_pyr_border (level l+1 never reads level l's border: edge taps clamp).
+#define ORBX_RS_TW 128
+#define ORBX_RS_TH 16
+
 __global__ void __launch_bounds__(256)
-k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level) {
+k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_s) {
+    extern __shared__ __align__(16) uint8_t smem_rs[];
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * ORBX_RS_TW, y0 = blockIdx.y * ORBX_RS_TH;
     const int frame = blockIdx.z;
-    if (wx * 4 >= L.pitch || r >= L.plane_rows) return;
     uint8_t* fbase = ws.pyr + (long long)frame * ws.pyr_stride;
-    const uint8_t* sroi = fbase + S.plane_off + (long long)ORBX_EDGE * S.pitch + ORBX_PADL;
-    const int y = reflect101(r - ORBX_EDGE, L.h);
-    const int2 yt = __ldg(ws.ytab + L.ytab_off + y);
-    const int b0 = yt.y & 0xffff, b1 = yt.y >> 16;
-    const uint8_t* s0 = sroi + (long long)yt.x * S.pitch;
-    const uint8_t* s1 = s0 + S.pitch;  // row h_src is the border row; its weight b1 is 0 there
+    const uint8_t* splane = fbase + S.plane_off;
+    const int2* xtab = ws.xtab + L.xtab_off;
+    const int2* ytab = ws.ytab + L.ytab_off;
+    const int x_last = min(x0 + ORBX_RS_TW, L.w) - 1, y_last = min(y0 + ORBX_RS_TH, L.h) - 1;
+    // source window (inclusive), second taps clamped into the level (their weight is 0 when clamped)
+    const int sx_lo = __ldg(&xtab[x0]).x, sx_hi = min(__ldg(&xtab[x_last]).x + 1, S.w - 1);
+    const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y_last]).x + 1, S.h - 1);
+    const int nrows = sy_hi - sy_lo + 1;
+    const int gcol = ORBX_PADL + sx_lo;            // plane byte column of the first staged pixel
+    const int al = gcol & 3;
+    const int nwords = (al + (sx_hi - sx_lo + 1) + 3) >> 2;
+    uint8_t* s_src = smem_rs;                                           // [src_rows_max][src_pitch_s]
+    uint16_t* s_h = reinterpret_cast<uint16_t*>(smem_rs + (((size_t)src_rows_max * src_pitch_s + 15) & ~(size_t)15));  // [src_rows_max][TW]
+    // ---- stage ----
+    {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al));
+        const int pw = S.pitch >> 2, spw = src_pitch_s >> 2;
+        const int total = nrows * nwords;
+        const unsigned wmagic = (1u << 20) / (unsigned)nwords + 1u;     // i / nwords for i < 2^12
+        for (int i = tid; i < total; i += 256) {
+            const int r = (int)(((unsigned)i * wmagic) >> 20);
+            const int wd = i - r * nwords;
+            reinterpret_cast<uint32_t*>(s_src)[r * spw + wd] = __ldg(g + r * pw + wd);
+        }
+    }
+    __syncthreads();
+    const bool area = __ldg(&xtab[x0]).y == -1;    // exact 2x2 decimation: OpenCV takes the INTER_AREA fast path
+    // ---- horizontal pass: thread owns one destination column ----
+    {
+        const int c = tid & (ORBX_RS_TW - 1);
+        const int2 xt = __ldg(&xtab[min(x0 + c, L.w - 1)]);
+        const int so = xt.x - sx_lo + al;
+        const int so1 = min(xt.x + 1, S.w - 1) - sx_lo + al;
+        const int a0 = xt.y & 0xffff, a1 = (xt.y >> 16) & 0xffff;
+        for (int r = tid >> 7; r < nrows; r += 2) {
+            const uint8_t* row = s_src + r * src_pitch_s;
+            const int v = area ? (row[so] + row[so1]) : ((row[so] * a0 + row[so1] * a1) >> 4);
+            s_h[r * ORBX_RS_TW + c] = (uint16_t)v;
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass: 4 columns x 1 row per item, one aligned word per store ----
+    uint8_t* droi = fbase + L.plane_off + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
+#pragma unroll
+    for (int it = 0; it < (ORBX_RS_TW / 4) * ORBX_RS_TH / 256; ++it) {
+        const int item = tid + it * 256;
+        const int cg = item & 31, ry = item >> 5;
+        const int x = x0 + 4 * cg, y = y0 + ry;
+        if (y > y_last || x > x_last) continue;
+        const int2 yt = __ldg(&ytab[y]);
+        const int r0 = yt.x - sy_lo, r1 = min(yt.x + 1, S.h - 1) - sy_lo;
+        const int b0 = yt.y & 0xffff, b1 = (yt.y >> 16) & 0xffff;
+        const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + r0 * ORBX_RS_TW + 4 * cg);
+        const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + r1 * ORBX_RS_TW + 4 * cg);
+        const int p0[4] = {(int)(h0.x & 0xffff), (int)(h0.x >> 16), (int)(h0.y & 0xffff), (int)(h0.y >> 16)};
+        const int p1[4] = {(int)(h1.x & 0xffff), (int)(h1.x >> 16), (int)(h1.y & 0xffff), (int)(h1.y >> 16)};
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = area ? ((p0[j] + p1[j] + 2) >> 2) : ((((b0 * p0[j]) >> 16) + ((b1 * p1[j]) >> 16) + 2) >> 2);
+            word |= (uint32_t)(v & 0xff) << (8 * j);
+        }
+        uint8_t* d = droi + (long long)y * L.pitch + x;
+        if (x + 3 <= x_last) {
+            *reinterpret_cast<uint32_t*>(d) = word;
+        } else {
+            for (int j = 0; x + j <= x_last; ++j) d[j] = (uint8_t)(word >> (8 * j));
+        }
+    }
+}
+
+// copyMakeBorder(BORDER_REFLECT_101) of levels >= 1 (:1193): one thread per aligned word of the border
+// frame (top/bottom bands and the left/right strips); a border pixel is the level pixel at the reflected
+// coordinate.  Level 0's border is written by k_pyr_level0.
+__global__ void __launch_bounds__(256)
+k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
+    const int level = blockIdx.y + 1;
+    const int frame = blockIdx.z;
+    const OrbxLevel& L = plan.lv[level];
+    const int pw = L.pitch >> 2;
+    const int rw0 = (ORBX_PADL + L.w) >> 2;            // first word touching the right border
+    const int nside = (ORBX_PADL >> 2) + (pw - rw0);   // words per middle row: left strip + right strip
+    const int nband = 2 * ORBX_EDGE * pw;              // top + bottom bands
+    const int total = nband + L.h * nside;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int r, wx;
+    if (i < nband) {
+        r = i / pw; wx = i - r * pw;
+        if (r >= ORBX_EDGE) r += L.h;
+    } else {
+        const int k = i - nband;
+        const int rr = k / nside, q = k - rr * nside;
+        r = ORBX_EDGE + rr;
+        wx = q < (ORBX_PADL >> 2) ? q : rw0 + (q - (ORBX_PADL >> 2));
+    }
+    uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
+    const uint8_t* roi = plane + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
+    const uint8_t* srow = roi + (long long)reflect101(r - ORBX_EDGE, L.h) * L.pitch;
     uint32_t word = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const int dx = wx * 4 + b - ORBX_PADL;
         uint32_t v = 0;
-        if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) {
-            const int x = reflect101(dx, L.w);
-            const int2 xt = __ldg(ws.xtab + L.xtab_off + x);
-            if (xt.y == -1) {  // exact 2x2 decimation: OpenCV takes the INTER_AREA fast path
-                v = (s0[xt.x] + s0[xt.x + 1] + s1[xt.x] + s1[xt.x + 1] + 2) >> 2;
-            } else {
-                const int a0 = xt.y & 0xffff, a1 = xt.y >> 16;
-                const int h0 = s0[xt.x] * a0 + s0[xt.x + 1] * a1;
-                const int h1 = s1[xt.x] * a0 + s1[xt.x + 1] * a1;
-                v = (uint32_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
-            }
-        }
-        word |= (v & 0xffu) << (8 * b);
+        if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = srow[reflect101(dx, L.w)];
+        word |= v << (8 * b);
     }
-    uint8_t* dst = fbase + L.plane_off;
-    *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch + wx * 4) = word;
+    *reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch + wx * 4) = word;
 }
 
 // =================================================================================================
@@ -191,9 +281,12 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     for (int i = lane; i < (tile_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
     __syncwarp();
 
-    const int iw = cw - 6, ih = ch - 6;
-    const int npix = iw * ih;
-    const unsigned magic = (1u << 24) / (unsigned)iw + 1u;  // idx / iw == (idx * magic) >> 24 (idx < 2^14, iw < 2^7)
+    const int ih = ch - 6;
+    // 4-pixel groups (aligned words) covering the interior columns [a+3, a+cw-3)
+    const int wq0 = (a + 3) >> 2;
+    const int ngrp = ((a + cw - 4) >> 2) - wq0 + 1;
+    const int ngroups = ngrp * ih;
+    const unsigned gmagic = (1u << 24) / (unsigned)ngrp + 1u;  // idx / ngrp == (idx * gmagic) >> 24 (idx < 2^13)
     // The reference detects at iniThFAST and re-runs the cell at minThFAST only if that found nothing
     // (:818-838); the same two phases here, the second one skipped when it cannot add anything.
     int qn = 0, n_out = 0, use_th = plan.ini_th;
@@ -202,20 +295,56 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
             if (plan.min_th >= plan.ini_th) break;
             use_th = plan.min_th;
         }
-        // ---- quick rejection over the interior, survivors compacted into `queue` ----
+        // ---- stage 1: branch-free bound from the vertical + horizontal ring pairs, 4 pixels per thread.
+        // A group is one aligned 32-bit word of row r; its up/down neighbours (rows r-3, r+3) are the same
+        // word of those rows, its left/right neighbours (x-3, x+3) come from a funnel shift of the row's
+        // adjacent words.  Bounds are evaluated two pixels at a time with 16-bit SIMD min/max.
         qn = 0;
-        for (int base = 0; base < npix; base += 32) {
-            const int idx = base + lane;
-            bool pass = false;
-            int p = 0;
-            if (idx < npix) {
-                const int r = (int)(((unsigned)idx * magic) >> 24);
-                p = (r + 3) * tp + a + (idx - r * iw) + 3;
-                pass = fast_quick(tile, p, tp, use_th);
+        {
+            const unsigned T1 = (unsigned)(use_th + 1) * 0x00010001u;
+            const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+            const int tpw = tp >> 2;
+            for (int base = 0; base < ngroups; base += 32) {
+                const int idx = base + lane;
+                unsigned m4 = 0;
+                int pbase = 0;
+                if (idx < ngroups) {
+                    const int gr = (int)(((unsigned)idx * gmagic) >> 24);
+                    const int wq = wq0 + (idx - gr * ngrp);
+                    const int wi = (gr + 3) * tpw + wq;
+                    const unsigned wc = t32[wi], wl = t32[wi - 1], wr = t32[wi + 1];
+                    const unsigned wu = t32[wi - 3 * tpw], wd = t32[wi + 3 * tpw];
+                    const unsigned lft = __funnelshift_r(wl, wc, 8), rgt = __funnelshift_r(wc, wr, 24);
+                    unsigned z = 0;
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const unsigned sel = hlf ? 0x4342u : 0x4140u;
+                        const unsigned c2 = __byte_perm(wc, 0, sel), u2 = __byte_perm(wu, 0, sel), d2 = __byte_perm(wd, 0, sel);
+                        const unsigned l2 = __byte_perm(lft, 0, sel), r2 = __byte_perm(rgt, 0, sel);
+                        const unsigned dk = __vmaxs2(__vmins2(u2, d2), __vmins2(l2, r2));
+                        const unsigned br = __vmins2(__vmaxs2(u2, d2), __vmaxs2(l2, r2));
+                        // lane-wise (c - dk > th) | (br - c > th): bit 15 of (x|0x8000) - (y + th + 1) is set iff x - y > th
+                        const unsigned z1 = (c2 | 0x80008000u) - (dk + T1);
+                        const unsigned z2 = (br | 0x80008000u) - (c2 + T1);
+                        const unsigned zz = (z1 | z2) & 0x80008000u;
+                        z |= ((zz >> 15) & 1u) << (2 * hlf) | ((zz >> 31) & 1u) << (2 * hlf + 1);
+                    }
+                    // keep only interior pixels of this word
+                    const int b0 = 4 * wq;
+                    unsigned valid = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) valid |= (unsigned)(b0 + j >= a + 3 && b0 + j < a + cw - 3) << j;
+                    m4 = z & valid;
+                    pbase = (gr + 3) * tp + b0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool pass = (m4 >> j) & 1u;
+                    const unsigned bal = __ballot_sync(ORBX_FULL_MASK, pass);
+                    if (pass) queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pbase + j);
+                    qn += __popc(bal);
+                }
             }
-            const unsigned bal = __ballot_sync(ORBX_FULL_MASK, pass);
-            if (pass) queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
-            qn += __popc(bal);
         }
         __syncwarp();
         // ---- exact corner measure for the queued pixels ----
@@ -586,10 +715,14 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 #define ORBX_BLUR_TW 128
 #define ORBX_BLUR_TH 32
 
+// Horizontal taps via IDP.4A on byte-aligned windows (funnel shifts of the staged words), vertical taps via
+// IDP.2A on 16-bit horizontal sums stored as row pairs (rows 2k, 2k+1 share one 32-bit word per column).
 __global__ void __launch_bounds__(256)
 k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
-    __shared__ __align__(16) uint8_t s_src[(ORBX_BLUR_TH + 6) * (ORBX_BLUR_TW + 8)];
-    __shared__ __align__(16) uint16_t s_h[(ORBX_BLUR_TH + 6) * ORBX_BLUR_TW];
+    constexpr int SROWS = ORBX_BLUR_TH + 6;          // 38 staged rows = 19 row pairs
+    constexpr int SW = (ORBX_BLUR_TW + 8) / 4;       // 34 words per staged row (cols x0-4 .. x0+131)
+    __shared__ __align__(16) uint32_t s_src[SROWS * SW];
+    __shared__ __align__(16) uint32_t s_h2[(SROWS / 2) * ORBX_BLUR_TW];
     int level = 0, tile = blockIdx.x;
     for (; level < plan.nlevels; ++level) {
         const int nt = ((plan.lv[level].w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW) * ((plan.lv[level].h + ORBX_BLUR_TH - 1) / ORBX_BLUR_TH);
@@ -601,45 +734,66 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int frame = blockIdx.y;
     if (ws.level_count[frame * plan.nlevels + level].x == 0) return;  // reference skips empty levels (:1122)
     const int tiles_x = (L.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW;
-    const int x0 = (tile % tiles_x) * ORBX_BLUR_TW, y0 = (tile / tiles_x) * ORBX_BLUR_TH;
-    const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
+    const int ty = tile / tiles_x;
+    const int x0 = (tile - ty * tiles_x) * ORBX_BLUR_TW, y0 = ty * ORBX_BLUR_TH;
+    const uint32_t* plane = reinterpret_cast<const uint32_t*>(ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off);
     const int tid = threadIdx.x;
-    constexpr int SW = (ORBX_BLUR_TW + 8) / 4;  // words per staged row
-    const int max_word = L.pitch / 4 - 1;
-    for (int i = tid; i < (ORBX_BLUR_TH + 6) * SW; i += 256) {
+    const int pw = L.pitch >> 2, max_word = pw - 1;
+    const int w0 = (ORBX_PADL + x0 - 4) >> 2;
+    for (int i = tid; i < SROWS * SW; i += 256) {
         const int r = i / SW, wd = i - r * SW;
         const int pr = min(ORBX_EDGE + y0 + r - 3, L.plane_rows - 1);
-        const int pw = min((ORBX_PADL + x0 - 4) / 4 + wd, max_word);
-        reinterpret_cast<uint32_t*>(s_src)[i] = __ldg(reinterpret_cast<const uint32_t*>(plane + (long long)pr * L.pitch) + pw);
+        s_src[i] = __ldg(plane + pr * pw + min(w0 + wd, max_word));
     }
     __syncthreads();
-    // horizontal pass: s_h[r][x] = sum k[i] * src[r][x + i - 3]; src column of output x is x + 4
-    for (int i = tid; i < (ORBX_BLUR_TH + 6) * (ORBX_BLUR_TW / 4); i += 256) {
-        const int r = i / (ORBX_BLUR_TW / 4), xq = i - r * (ORBX_BLUR_TW / 4);
-        const uint8_t* s = s_src + r * (ORBX_BLUR_TW + 8) + xq * 4 + 1;  // src[x-3] for x = 4*xq
-        int v[10];
+    // ---- horizontal: item = (row pair, 4-pixel group); output x reads staged bytes x+1 .. x+7 ----
+    const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+    for (int i = tid; i < (SROWS / 2) * (ORBX_BLUR_TW / 4); i += 256) {
+        const int rp = i >> 5, xq = i & 31;
+        uint32_t h[2][4];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) v[j] = s[j];
-        uint16_t* hrow = s_h + r * ORBX_BLUR_TW + xq * 4;
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t* s = s_src + (2 * rp + k) * SW + xq;
+            const uint32_t a = s[0], b = s[1], c = s[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            hrow[j] = (uint16_t)(18 * (v[j] + v[j + 6]) + 34 * (v[j + 1] + v[j + 5]) + 48 * (v[j + 2] + v[j + 4]) + 56 * v[j + 3]);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t lo = j == 3 ? b : __funnelshift_r(a, b, 8 * (j + 1));
+                const uint32_t hi = j == 3 ? c : __funnelshift_r(b, c, 8 * (j + 1));
+                h[k][j] = __dp4a(lo, K0, __dp4a(hi, K1, 0u));
+            }
+        }
+        uint4 o;
+        o.x = h[0][0] | (h[1][0] << 16); o.y = h[0][1] | (h[1][1] << 16);
+        o.z = h[0][2] | (h[1][2] << 16); o.w = h[0][3] | (h[1][3] << 16);
+        *reinterpret_cast<uint4*>(s_h2 + rp * ORBX_BLUR_TW + 4 * xq) = o;
     }
     __syncthreads();
+    // ---- vertical: item = (two output rows 2q, 2q+1) x (4 pixels); both rows use row pairs q .. q+3 ----
+    const unsigned WE01 = 18u | (34u << 8) | (48u << 16) | (56u << 24), WE23 = 48u | (34u << 8) | (18u << 16);
+    const unsigned WO01 = (18u << 8) | (34u << 16) | (48u << 24), WO23 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
     uint8_t* out = ws.blur + (long long)frame * ws.blur_stride + L.blur_off;
-    for (int i = tid; i < ORBX_BLUR_TH * (ORBX_BLUR_TW / 4); i += 256) {
-        const int r = i / (ORBX_BLUR_TW / 4), xq = i - r * (ORBX_BLUR_TW / 4);
-        const int y = y0 + r, x = x0 + xq * 4;
+#pragma unroll
+    for (int it = 0; it < (ORBX_BLUR_TH / 2) * (ORBX_BLUR_TW / 4) / 256; ++it) {
+        const int i = tid + it * 256;
+        const int q = i >> 5, xq = i & 31;
+        const int y = y0 + 2 * q, x = x0 + 4 * xq;
         if (y >= L.h || x >= L.blur_pitch) continue;
-        uint32_t word = 0;
+        const uint4 p0 = *reinterpret_cast<const uint4*>(s_h2 + (q + 0) * ORBX_BLUR_TW + 4 * xq);
+        const uint4 p1 = *reinterpret_cast<const uint4*>(s_h2 + (q + 1) * ORBX_BLUR_TW + 4 * xq);
+        const uint4 p2 = *reinterpret_cast<const uint4*>(s_h2 + (q + 2) * ORBX_BLUR_TW + 4 * xq);
+        const uint4 p3 = *reinterpret_cast<const uint4*>(s_h2 + (q + 3) * ORBX_BLUR_TW + 4 * xq);
+        const uint32_t a0[4] = {p0.x, p0.y, p0.z, p0.w}, a1[4] = {p1.x, p1.y, p1.z, p1.w};
+        const uint32_t a2[4] = {p2.x, p2.y, p2.z, p2.w}, a3[4] = {p3.x, p3.y, p3.z, p3.w};
+        uint32_t we = 0, wo = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint16_t* h = s_h + r * ORBX_BLUR_TW + xq * 4 + j;
-            const uint32_t acc = 18u * ((uint32_t)h[0] + h[6 * ORBX_BLUR_TW]) + 34u * ((uint32_t)h[ORBX_BLUR_TW] + h[5 * ORBX_BLUR_TW]) +
-                                 48u * ((uint32_t)h[2 * ORBX_BLUR_TW] + h[4 * ORBX_BLUR_TW]) + 56u * (uint32_t)h[3 * ORBX_BLUR_TW];
-            word |= ((acc + 32768u) >> 16) << (8 * j);
+            const uint32_t ve = __dp2a_hi(a3[j], WE23, __dp2a_lo(a2[j], WE23, __dp2a_hi(a1[j], WE01, __dp2a_lo(a0[j], WE01, 32768u))));
+            const uint32_t vo = __dp2a_hi(a3[j], WO23, __dp2a_lo(a2[j], WO23, __dp2a_hi(a1[j], WO01, __dp2a_lo(a0[j], WO01, 32768u))));
+            we |= (ve >> 16) << (8 * j);
+            wo |= (vo >> 16) << (8 * j);
         }
-        *reinterpret_cast<uint32_t*>(out + (long long)y * L.blur_pitch + x) = word;
+        *reinterpret_cast<uint32_t*>(out + (long long)y * L.blur_pitch + x) = we;
+        if (y + 1 < L.h) *reinterpret_cast<uint32_t*>(out + (long long)(y + 1) * L.blur_pitch + x) = wo;
     }
 }
 
