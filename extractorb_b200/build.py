@@ -49,5 +49,34 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_host(force=False, verbose=False):
+    """The C++ drop-in class (include/ORBextractor.h) against the compat cv types, plus the test driver."""
+    build_cuda(force=False)
+    inc = os.path.join(HERE, "..", "include")
+    src = os.path.join(CSRC, "ORBextractor.cpp")
+    deps = [src, os.path.join(inc, "ORBextractor.h"), os.path.join(inc, "orbx_cv_compat.hpp"), os.path.join(inc, "orbx.h"), LIB]
+    cxx = shutil.which("g++") or "g++"
+    if force or _stale(HOST_LIB, deps):
+        cmd = [cxx, "-O2", "-std=c++11", "-fPIC", "-shared", "-DORBX_FORCE_CV_COMPAT", "-I", inc, "-o", HOST_LIB, src,
+               "-L", HERE, "-lextractorb_cuda", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed (libORBextractor.so)")
+    demo_src = os.path.join(HERE, "..", "tests", "cpp", "dropin_main.cpp")
+    demo = os.path.join(HERE, "..", "tests", "cpp", "dropin_main")
+    if os.path.exists(demo_src) and (force or _stale(demo, [demo_src, HOST_LIB])):
+        cmd = [cxx, "-O2", "-std=c++11", "-pthread", "-DORBX_FORCE_CV_COMPAT", "-I", inc, "-o", demo, demo_src, "-L", HERE,
+               "-lORBextractor", "-lextractorb_cuda", "-Wl,-rpath,$ORIGIN/../../extractorb_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed (dropin_main)")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv, verbose=True))

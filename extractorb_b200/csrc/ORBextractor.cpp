@@ -1,0 +1,196 @@
+// extractorb_b200/csrc/ORBextractor.cpp -- host side of the drop-in class declared in include/ORBextractor.h.
+// It only unwraps cv::InputArray / cv::OutputArray, sizes the caller's containers and forwards to the
+// C-ABI (include/orbx.h); all pixel work happens in libextractorb_cuda.so.  Reference being replaced:
+// /root/reference/src/orb_extractor/ORBextractor.cc (operator() :1078-1162, constructor :408-475).
+#include "../../include/ORBextractor.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/orbx.h"
+
+namespace ORB_SLAM3 {
+
+namespace {
+const signed char kPatternTable[1024] = {
+#include "orb_pattern.inc"
+};
+static_assert(sizeof(cv::KeyPoint) == sizeof(OrbxKeyPoint), "cv::KeyPoint must be the 28-byte layout the C-ABI writes");
+const int kEdge = 19;  // EDGE_THRESHOLD, reference :72
+}  // namespace
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      mpHandle(nullptr), mnDevice(0), mbDownloadPyramid(true) {
+    if (const char* env = std::getenv("ORBX_DEVICE")) mnDevice = std::atoi(env);
+    // The tables are plain host arithmetic; they are computed by the library's constructor code so that
+    // there is a single implementation, but a missing GPU must not make the constructor throw: ORB-SLAM3
+    // constructs extractors while parsing its settings (reference src/Tracking.cc:768-774).
+    mvScaleFactor.assign(nlevels > 0 ? nlevels : 0, 1.f);
+    mvInvScaleFactor = mvLevelSigma2 = mvInvLevelSigma2 = mvScaleFactor;
+    mnFeaturesPerLevel.assign(mvScaleFactor.size(), 0);
+    umax.assign(16, 0);
+    mvImagePyramid.resize(mvScaleFactor.size());
+    const cv::Point* p0 = nullptr;
+    (void)p0;
+    pattern.reserve(512);
+    for (int i = 0; i < 512; ++i) pattern.push_back(cv::Point(kPatternTable[2 * i], kPatternTable[2 * i + 1]));
+    EnsureHandle();
+}
+
+ORBextractor::~ORBextractor() {
+    if (mpHandle) orbx_destroy(mpHandle);
+}
+
+void ORBextractor::SetDevice(int device) {
+    if (device == mnDevice && mpHandle) return;
+    if (mpHandle) { orbx_destroy(mpHandle); mpHandle = nullptr; }
+    mnDevice = device;
+    EnsureHandle();
+}
+
+OrbxHandle* ORBextractor::NativeHandle() {
+    EnsureHandle();
+    return mpHandle;
+}
+
+bool ORBextractor::EnsureHandle() {
+    if (mpHandle) return true;
+    OrbxParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.nfeatures = nfeatures; prm.scale_factor = (float)scaleFactor; prm.nlevels = nlevels;
+    prm.ini_th_fast = iniThFAST; prm.min_th_fast = minThFAST;
+    const int rc = orbx_create(&prm, mnDevice, &mpHandle);
+    if (rc != ORBX_OK) {
+        mpHandle = nullptr;
+        mLastError = std::string("orbx_create: ") + orbx_status_string(rc);
+        return false;
+    }
+    orbx_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                    mnFeaturesPerLevel.data(), umax.data());
+    mLastError.clear();
+    return true;
+}
+
+bool ORBextractor::DownloadPyramid() {
+    for (int l = 0; l < nlevels; ++l) {
+        int w = 0, h = 0;
+        if (orbx_get_level_size(mpHandle, l, &w, &h) != ORBX_OK) return false;
+        cv::Mat temp(cv::Size(w + 2 * kEdge, h + 2 * kEdge), CV_8UC1);                    // reference :1173-1175
+        if (orbx_get_pyramid_level(mpHandle, 0, l, temp.data, temp.step, 1) != ORBX_OK) return false;
+        mvImagePyramid[l] = temp(cv::Rect(kEdge, kEdge, w, h));                          // :1177
+    }
+    return true;
+}
+
+int ORBextractor::Extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors,
+                          std::vector<int>& vLappingArea, std::vector<std::vector<cv::KeyPoint> >* allLevels) {
+    if (_image.empty()) return -1;                                                       // :1083
+    cv::Mat image = _image.getMat();
+    if (image.type() != CV_8UC1) { mLastError = "image must be CV_8UC1"; return -1; }     // reference: assert, :1087
+    if (vLappingArea.size() < 2) { mLastError = "vLappingArea needs two entries"; return -1; }
+    if (!EnsureHandle()) return -1;
+    const int cap = orbx_max_keypoints(mpHandle, image.cols, image.rows);
+    if (cap < 0) { mLastError = orbx_last_error(mpHandle); return -1; }
+    std::vector<cv::KeyPoint> kps((size_t)cap);
+    std::vector<unsigned char> desc((size_t)cap * 32);
+    int n = 0, mono = 0;
+    const int rc = orbx_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0], vLappingArea[1],
+                                reinterpret_cast<OrbxKeyPoint*>(kps.data()), desc.data(), cap, &n, &mono);
+    if (rc != ORBX_OK) { mLastError = orbx_last_error(mpHandle); return -1; }
+    mLastError.clear();
+    if (n == 0) {
+        _descriptors.release();                                                          // :1102-1103
+    } else {
+        _descriptors.create(n, 32, CV_8U);                                               // :1106
+        cv::Mat d = _descriptors.getMat();
+        for (int r = 0; r < n; ++r) std::memcpy(d.ptr(r), desc.data() + (size_t)r * 32, 32);
+    }
+    kps.resize((size_t)n);
+    _keypoints.swap(kps);                                                                // fresh vector, :1112
+    if (allLevels) {                                                                     // :1094 (level coordinates)
+        allLevels->assign((size_t)nlevels, std::vector<cv::KeyPoint>());
+        for (int l = 0; l < nlevels; ++l) {
+            int nl = 0;
+            orbx_get_level_keypoints(mpHandle, 0, l, nullptr, 0, &nl);
+            (*allLevels)[l].resize((size_t)nl);
+            if (nl) orbx_get_level_keypoints(mpHandle, 0, l, reinterpret_cast<OrbxKeyPoint*>((*allLevels)[l].data()), nl, &nl);
+        }
+    }
+    if (mbDownloadPyramid && !DownloadPyramid()) { mLastError = orbx_last_error(mpHandle); return -1; }
+    return mono;                                                                         // monoIndex, :1161
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    return Extract(_image, _keypoints, _descriptors, vLappingArea, nullptr);
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea,
+                             std::vector<std::vector<cv::KeyPoint> >& allLevelsKeypoints) {
+    return Extract(_image, _keypoints, _descriptors, vLappingArea, &allLevelsKeypoints);
+}
+
+void ORBextractor::ComputePyramid(cv::Mat image) {
+    if (image.empty() || image.type() != CV_8UC1 || !EnsureHandle()) return;
+    if (orbx_compute_pyramid(mpHandle, image.data, image.cols, image.rows, (size_t)image.step) != ORBX_OK) {
+        mLastError = orbx_last_error(mpHandle);
+        return;
+    }
+    mLastError.clear();
+    DownloadPyramid();
+}
+
+void ORBextractor::ComputeKeyPointsOctTree(std::vector<std::vector<cv::KeyPoint> >& allKeypoints) {
+    allKeypoints.assign((size_t)nlevels, std::vector<cv::KeyPoint>());                   // :775
+    if (!EnsureHandle()) return;
+    if (orbx_compute_keypoints_octtree(mpHandle) != ORBX_OK) { mLastError = orbx_last_error(mpHandle); return; }
+    mLastError.clear();
+    for (int l = 0; l < nlevels; ++l) {
+        int nl = 0;
+        orbx_get_level_keypoints(mpHandle, 0, l, nullptr, 0, &nl);
+        allKeypoints[l].resize((size_t)nl);
+        if (nl) orbx_get_level_keypoints(mpHandle, 0, l, reinterpret_cast<OrbxKeyPoint*>(allKeypoints[l].data()), nl, &nl);
+    }
+}
+
+std::vector<cv::KeyPoint> ORBextractor::DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX,
+                                                          const int& maxX, const int& minY, const int& maxY, const int& N,
+                                                          const int& /*level*/) {
+    std::vector<cv::KeyPoint> out;
+    if (!EnsureHandle()) return out;
+    const int nIni = (int)std::lround((double)(maxX - minX) / (double)(maxY - minY > 0 ? maxY - minY : 1));
+    const int cap = std::max(N + 2, 4 * std::max(nIni, 1)) + 8;
+    out.resize((size_t)cap);
+    int n = 0;
+    const int rc = orbx_distribute_octtree(mpHandle, reinterpret_cast<const OrbxKeyPoint*>(vToDistributeKeys.data()),
+                                           (int)vToDistributeKeys.size(), minX, maxX, minY, maxY, N,
+                                           reinterpret_cast<OrbxKeyPoint*>(out.data()), cap, &n);
+    if (rc != ORBX_OK) { mLastError = orbx_last_error(mpHandle); out.clear(); return out; }
+    mLastError.clear();
+    out.resize((size_t)n);
+    return out;
+}
+
+// Geometry of one quadtree split (reference :486-542); host-side, for callers that use the node type.
+void ExtractorNode::DivideNode(ExtractorNode& n1, ExtractorNode& n2, ExtractorNode& n3, ExtractorNode& n4) {
+    const int halfX = (int)std::ceil(static_cast<float>(UR.x - UL.x) / 2);
+    const int halfY = (int)std::ceil(static_cast<float>(BR.y - UL.y) / 2);
+    const int xm = UL.x + halfX, ym = UL.y + halfY;
+    ExtractorNode* child[4] = {&n1, &n2, &n3, &n4};
+    n1.UL = UL;                     n1.UR = cv::Point2i(xm, UL.y);   n1.BL = cv::Point2i(UL.x, ym);  n1.BR = cv::Point2i(xm, ym);
+    n2.UL = n1.UR;                  n2.UR = UR;                      n2.BL = n1.BR;                  n2.BR = cv::Point2i(UR.x, ym);
+    n3.UL = n1.BL;                  n3.UR = n1.BR;                   n3.BL = BL;                     n3.BR = cv::Point2i(xm, BL.y);
+    n4.UL = n3.UR;                  n4.UR = n2.BR;                   n4.BL = n3.BR;                  n4.BR = BR;
+    for (int c = 0; c < 4; ++c) { child[c]->vKeys.clear(); child[c]->vKeys.reserve(vKeys.size()); child[c]->bNoMore = false; }
+    for (size_t i = 0; i < vKeys.size(); ++i) {
+        const cv::KeyPoint& kp = vKeys[i];
+        const int c = (kp.pt.x < xm ? 0 : 1) + (kp.pt.y < ym ? 0 : 2);
+        child[c]->vKeys.push_back(kp);
+    }
+    for (int c = 0; c < 4; ++c) if (child[c]->vKeys.size() == 1) child[c]->bNoMore = true;
+}
+
+}  // namespace ORB_SLAM3

@@ -70,9 +70,10 @@ struct OrbxHandle {
     int ws_frames = 0;
     OrbxWs ws{};
     int8_t* d_pattern = nullptr;
-    uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
-    void* d_out = nullptr; size_t d_out_bytes = 0;
-    uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned
+    uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
+    void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
+    cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // profiling
     std::vector<StageEvents> events;
     size_t events_used = 0;
@@ -319,7 +320,8 @@ int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
     ORBX_CUDA(cudaMalloc(&w.kprec, (size_t)P.kp_total * frames * sizeof(OrbxKpRec)));
     ORBX_CUDA(cudaMalloc(&w.cand_count, (size_t)P.nlevels * frames * sizeof(int)));
     ORBX_CUDA(cudaMalloc(&w.level_count, (size_t)P.nlevels * frames * sizeof(int2)));
-    ORBX_CUDA(cudaMalloc(&w.flags, (size_t)frames * sizeof(int)));
+    ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
+    ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
     w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.pattern = h->d_pattern;
@@ -390,7 +392,6 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     if (se) ORBX_CUDA(cudaEventRecord(se->ev[1], st));
     if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
-        ORBX_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)nf * sizeof(int), st));
         k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
@@ -450,12 +451,12 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
     return ORBX_OK;
 }
 
-// Did any frame of the last group overflow its candidate workspace?
-int check_overflow(OrbxHandle* h, int nf, bool* overflow) {
-    std::vector<int> flags(nf);
-    ORBX_CUDA(cudaMemcpy(flags.data(), h->ws.flags, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost));
-    *overflow = false;
-    for (int f : flags) if (f & 1) *overflow = true;
+// Did any frame since the last check overflow its candidate workspace?  (Reads and clears the flag word.)
+int check_overflow(OrbxHandle* h, bool* overflow) {
+    int flag = 0;
+    ORBX_CUDA(cudaMemcpy(&flag, h->ws.flags, sizeof(int), cudaMemcpyDeviceToHost));
+    *overflow = (flag & 1) != 0;
+    if (flag) ORBX_CUDA(cudaMemset(h->ws.flags, 0, sizeof(int)));
     return ORBX_OK;
 }
 
@@ -499,6 +500,13 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     build_ctor_tables(h);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern, sizeof(kPatternHost));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { delete h; return ORBX_ERR_CUDA; }
@@ -513,8 +521,14 @@ void orbx_destroy(OrbxHandle* h) {
     drop_plans(h);
     free_plan(h->dist_plan);
     cudaFree(h->d_pattern); cudaFree(h->d_in); cudaFree(h->d_out);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -560,63 +574,63 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         if (rc != ORBX_OK) return rc;
         rc = set_kernel_attrs(h, pe);
         if (rc != ORBX_OK) return rc;
-        // device-side output block for host outputs: [kps | desc | counts] per group
+        // Host buffers are pipelined through two staging slots: copy-in (s_in), kernels (st), copy-out (s_out).
+        const bool host_in = in_mem == ORBX_MEM_HOST, host_out = out_mem == ORBX_MEM_HOST;
         const size_t kp_bytes = (size_t)cap_per_frame * sizeof(OrbxKeyPoint), ds_bytes = (size_t)cap_per_frame * 32;
-        uint8_t *o_kps = nullptr, *o_desc = nullptr;
-        int32_t* o_counts = nullptr;
-        if (out_mem == ORBX_MEM_HOST) {
-            const size_t need = (kp_bytes + ds_bytes + 8) * (size_t)group + 256;
-            rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, need, false);
-            if (rc != ORBX_OK) return rc;
-            o_kps = (uint8_t*)h->d_out;
-            o_desc = o_kps + align_up((long long)kp_bytes * group, 64);
-            o_counts = (int32_t*)(o_desc + align_up((long long)ds_bytes * group, 64));
-        }
-        if (in_mem == ORBX_MEM_HOST) {
-            rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)width * height * group, false);
-            if (rc != ORBX_OK) return rc;
-        }
-        bool overflow = false;
-        for (int f0 = 0; f0 < n_frames; f0 += group) {
+        const size_t in_slot = (size_t)align_up((long long)width * height * group, 256);
+        const size_t o_kps_off = 0, o_desc_off = (size_t)align_up((long long)kp_bytes * group, 256);
+        const size_t o_cnt_off = o_desc_off + (size_t)align_up((long long)ds_bytes * group, 256);
+        const size_t out_slot = o_cnt_off + (size_t)align_up(8ll * group, 256);
+        if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, 2 * out_slot, false); if (rc != ORBX_OK) return rc; }
+        if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, 2 * in_slot, false); if (rc != ORBX_OK) return rc; }
+        int gi = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += group, ++gi) {
             const int nf = std::min(group, n_frames - f0);
+            const int slot = gi & 1;
             const uint8_t* d_imgs;
             long long rs, fs;
-            if (in_mem == ORBX_MEM_HOST) {
+            if (host_in) {
+                uint8_t* dst = h->d_in + (size_t)slot * in_slot;
+                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // slot's previous group consumed
                 if (row_stride == (size_t)width && (nf == 1 || frame_stride == (size_t)width * height)) {
-                    ORBX_CUDA(cudaMemcpyAsync(h->d_in, images + (size_t)f0 * frame_stride, (size_t)width * height * nf,
-                                              cudaMemcpyHostToDevice, st));
+                    ORBX_CUDA(cudaMemcpyAsync(dst, images + (size_t)f0 * frame_stride, (size_t)width * height * nf, cudaMemcpyHostToDevice, h->s_in));
                 } else {
                     for (int f = 0; f < nf; ++f)
-                        ORBX_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)f * width * height, (size_t)width,
-                                                    images + (size_t)(f0 + f) * frame_stride, row_stride, (size_t)width,
-                                                    (size_t)height, cudaMemcpyHostToDevice, st));
+                        ORBX_CUDA(cudaMemcpy2DAsync(dst + (size_t)f * width * height, (size_t)width, images + (size_t)(f0 + f) * frame_stride,
+                                                    row_stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->s_in));
                 }
-                d_imgs = h->d_in; rs = width; fs = (long long)width * height;
+                ORBX_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+                ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[slot], 0));
+                d_imgs = dst; rs = width; fs = (long long)width * height;
             } else {
                 d_imgs = images + (size_t)f0 * frame_stride; rs = (long long)row_stride; fs = (long long)frame_stride;
             }
-            if (out_mem == ORBX_MEM_HOST) {
-                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps ? o_kps : nullptr, desc ? o_desc : nullptr,
-                                  cap_per_frame, o_counts, 0, STAGES_ALL);
+            if (host_out) {
+                uint8_t* ob = (uint8_t*)h->d_out + (size_t)slot * out_slot;
+                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[slot], 0));         // slot's previous results copied out
+                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
+                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL);
                 if (rc != ORBX_OK) return rc;
-                if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, o_kps, kp_bytes * nf, cudaMemcpyDeviceToHost, st));
-                if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, o_desc, ds_bytes * nf, cudaMemcpyDeviceToHost, st));
-                if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, o_counts, 8 * (size_t)nf, cudaMemcpyDeviceToHost, st));
-                ORBX_CUDA(cudaStreamSynchronize(st));   // staging buffers are reused by the next group
+                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], st));
+                ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+                if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
+                ORBX_CUDA(cudaEventRecord(h->ev_d2h[slot], h->s_out));
             } else {
                 rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL);
                 if (rc != ORBX_OK) return rc;
+                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], st));
             }
-            // the workspace is reused by the next group: order the overflow check behind this group's kernels
-            ORBX_CUDA(cudaStreamSynchronize(st));
-            bool ov = false;
-            rc = check_overflow(h, nf, &ov);
-            if (rc != ORBX_OK) return rc;
-            if (ov) { overflow = true; break; }
         }
+        ORBX_CUDA(cudaStreamSynchronize(st));
+        if (host_out) ORBX_CUDA(cudaStreamSynchronize(h->s_out));
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
+        bool overflow = false;
+        rc = check_overflow(h, &overflow);
+        if (rc != ORBX_OK) return rc;
         if (!overflow) return ORBX_OK;
-        // grow the candidate workspace and run again (results of a partial run are overwritten)
+        // grow the candidate workspace and run the call again (every output is rewritten)
         if (attempt >= 6) return fail(h, ORBX_ERR_CANDIDATE_OVERFLOW, "FAST candidate workspace overflow after regrowth");
         h->cand_per_cell *= 4;
         drop_plans(h);
@@ -664,7 +678,7 @@ static int run_stages_single(OrbxHandle* h, const uint8_t* image, int width, int
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
         if (!(stages & STAGES_KEYPOINTS)) return ORBX_OK;
         bool ov = false;
-        rc = check_overflow(h, 1, &ov);
+        rc = check_overflow(h, &ov);
         if (rc != ORBX_OK) return rc;
         if (!ov) return ORBX_OK;
         (void)attempt;

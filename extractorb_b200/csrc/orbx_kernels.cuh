@@ -382,7 +382,7 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     if (lane == 0) slot0 = atomicAdd(counter, n_out);
     slot0 = __shfl_sync(ORBX_FULL_MASK, slot0, 0);
     if (slot0 + n_out > L.cand_cap) {
-        if (lane == 0) atomicOr(ws.flags + frame, 1);
+        if (lane == 0) atomicOr(ws.flags, 1);
     }
     uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
     const unsigned tpmagic = (1u << 24) / (unsigned)tp + 1u;  // p / tp (p < 2^14, tp <= 136)

@@ -86,7 +86,7 @@ struct OrbxWs {
     OrbxKpRec* kprec;      int kp_stride;             // records
     int* cand_count;       // [frame][level]
     int2* level_count;     // [frame][level] = {n, n_lapping}
-    int* flags;            // [frame] bit0: candidate overflow
+    int* flags;            // one word, bit0: some frame overflowed its candidate workspace
     const int2* xtab;      // resize: {src offset, a0 | a1<<16}
     const int2* ytab;
     const OrbxCell* cells;

@@ -100,8 +100,9 @@ ORBX_API int orbx_extract(OrbxHandle* h, const uint8_t* image, int width, int he
 /* The same path over n_frames independent frames (the data-parallel form: one launch group per
  * max_batch frames).  images/kps/desc/counts live in `in_mem`/`out_mem` memory (ORBX_MEM_*); frame f's
  * outputs start at kps + f*cap_per_frame, desc + f*cap_per_frame*32, counts + 2*f ({n, mono}).
- * `stream` is a cudaStream_t (NULL -> the handle's own stream).  With device outputs the call is
- * asynchronous on that stream; with any host buffer it returns after the results have landed. */
+ * `stream` is the cudaStream_t the kernels are launched on (NULL -> the handle's own stream).  Host
+ * buffers (pinned for full speed) are pipelined group by group: H2D of group g+1, kernels of group g and D2H
+ * of group g-1 overlap on three streams.  The call returns after all results have landed. */
 ORBX_API int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height,
                        size_t row_stride, size_t frame_stride, int lap0, int lap1,
                        OrbxKeyPoint* kps, uint8_t* desc, int cap_per_frame, int32_t* counts, int out_mem,

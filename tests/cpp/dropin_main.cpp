@@ -1,0 +1,99 @@
+// tests/cpp/dropin_main.cpp -- drives the drop-in C++ class exactly like oracle/ref_main.cpp drives the
+// unmodified reference (same frame / result file formats), so that tests/test_cpp_dropin.py can compare the
+// two programs' outputs byte for byte.  Also exercises the accessors, the stage-wise public methods and the
+// two-thread stereo pattern of the reference's caller (src/Frame.cc:109-112).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "ORBExtractor.h"   // global-namespace spelling (reference inc/ORBExtractor.h), includes ORBextractor.h
+
+static bool load_frames(const char* path, int& n, int& w, int& h, std::vector<uint8_t>& data) {
+    FILE* fp = std::fopen(path, "rb");
+    if (!fp) return false;
+    int32_t hdr[4];
+    if (std::fread(hdr, 4, 4, fp) != 4 || hdr[0] != 0x4642524f) { std::fclose(fp); return false; }
+    n = hdr[1]; w = hdr[2]; h = hdr[3];
+    data.resize((size_t)n * w * h);
+    bool ok = std::fread(data.data(), 1, data.size(), fp) == data.size();
+    std::fclose(fp);
+    return ok;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 12 || std::strcmp(argv[1], "run")) {
+        std::fprintf(stderr, "usage: %s run <frames.orbf> <out.orbr> nfeatures scale nlevels ini min lap0 lap1 dump_pyr [mode]\n", argv[0]);
+        return 2;
+    }
+    int n, w, h;
+    std::vector<uint8_t> frames;
+    if (!load_frames(argv[2], n, w, h, frames)) { std::fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    const int nfeatures = std::atoi(argv[4]); const float scale = (float)std::atof(argv[5]); const int nlevels = std::atoi(argv[6]);
+    const int ini = std::atoi(argv[7]), mn = std::atoi(argv[8]), lap0 = std::atoi(argv[9]), lap1 = std::atoi(argv[10]);
+    const int dump = std::atoi(argv[11]);
+    const char* mode = argc > 12 ? argv[12] : "six";
+    FILE* out = std::fopen(argv[3], "wb");
+    if (!out) return 1;
+    int32_t hdr[4] = {0x5242524f, n, nlevels, dump};
+    std::fwrite(hdr, 4, 4, out);
+
+    ORBextractor ex(nfeatures, scale, nlevels, ini, mn);          // global alias of ORB_SLAM3::ORBextractor
+    if (ex.GetLevels() != nlevels || (int)ex.GetScaleFactors().size() != nlevels || ex.GetScaleFactor() != scale) return 3;
+    for (int i = 0; i < n; ++i) {
+        cv::Mat img(h, w, CV_8UC1, frames.data() + (size_t)i * w * h);
+        std::vector<cv::KeyPoint> kps;
+        cv::Mat desc;
+        std::vector<int> lap = {lap0, lap1};
+        std::vector<std::vector<cv::KeyPoint> > lvl;
+        int ret;
+        if (!std::strcmp(mode, "five")) {
+            // the north-star signature (reference inc/ORBExtractor.h:55-56) + the demo's direct stage calls
+            ret = ex(img, cv::Mat(), kps, desc, lap);
+            ORBextractor ex2(nfeatures, scale, nlevels, ini, mn);
+            ex2.ComputePyramid(img);
+            ex2.ComputeKeyPointsOctTree(lvl);
+        } else if (!std::strcmp(mode, "threads")) {
+            // stereo pattern: two instances, two host threads, same image -> must agree with each other
+            ORB_SLAM3::ORBextractor right(nfeatures, scale, nlevels, ini, mn);
+            std::vector<cv::KeyPoint> kps_r; cv::Mat desc_r; std::vector<std::vector<cv::KeyPoint> > lvl_r;
+            std::vector<int> lap_r = lap;
+            int ret_r = -7;
+            std::thread tl([&]() { ret = ex(img, cv::Mat(), kps, desc, lap, lvl); });
+            std::thread tr([&]() { ret_r = right(img, cv::Mat(), kps_r, desc_r, lap_r, lvl_r); });
+            tl.join(); tr.join();
+            if (ret != ret_r || kps.size() != kps_r.size() ||
+                (kps.size() && std::memcmp(kps.data(), kps_r.data(), kps.size() * sizeof(cv::KeyPoint)))) return 4;
+        } else {
+            ret = ex(img, cv::Mat(), kps, desc, lap, lvl);
+        }
+        if (ret < 0 && !ex.LastError().empty()) std::fprintf(stderr, "extractor: %s\n", ex.LastError().c_str());
+        int32_t cnt = (int32_t)kps.size();
+        std::fwrite(&ret, 4, 1, out);
+        std::fwrite(&cnt, 4, 1, out);
+        for (int l = 0; l < nlevels; ++l) {
+            int32_t c = l < (int)lvl.size() ? (int32_t)lvl[l].size() : 0;
+            std::fwrite(&c, 4, 1, out);
+        }
+        if (cnt) {
+            std::fwrite(kps.data(), sizeof(cv::KeyPoint), (size_t)cnt, out);
+            if (desc.rows != cnt || desc.cols != 32) return 5;
+            for (int r = 0; r < cnt; ++r) std::fwrite(desc.ptr(r), 1, 32, out);
+        } else if (!desc.empty()) return 6;
+        for (size_t l = 0; l < lvl.size(); ++l)
+            if (!lvl[l].empty()) std::fwrite(lvl[l].data(), sizeof(cv::KeyPoint), lvl[l].size(), out);
+        if (dump) {
+            for (int l = 0; l < nlevels; ++l) {
+                const cv::Mat& m = ex.mvImagePyramid[l];           // ROI at (19,19) of the bordered buffer
+                int32_t wh[2] = {m.cols, m.rows};
+                std::fwrite(wh, 4, 2, out);
+                const uint8_t* base = m.data - 19 * m.step - 19;
+                for (int r = 0; r < m.rows + 38; ++r) std::fwrite(base + (size_t)r * m.step, 1, (size_t)m.cols + 38, out);
+            }
+        }
+    }
+    std::fclose(out);
+    return 0;
+}

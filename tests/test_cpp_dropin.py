@@ -1,0 +1,82 @@
+"""The C++ drop-in class (include/ORBextractor.h, ORB_SLAM3::ORBextractor + the global-namespace alias of
+include/ORBExtractor.h) driven by tests/cpp/dropin_main.cpp, the twin of oracle/ref_main.cpp: both programs
+read the same frame file and write the same result file, so the comparison is program against program."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from common import kp_bytes_equal, desc_bit_agreement
+
+DEMO = os.path.join(ROOT, "tests", "cpp", "dropin_main")
+
+
+@pytest.fixture(scope="module")
+def demo():
+    from extractorb_b200 import build
+    build.build_host()
+    assert os.access(DEMO, os.X_OK)
+    return DEMO
+
+
+def run_demo(demo, frames, p, mode="six", dump=True):
+    from oracle import refio
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.orbf"), os.path.join(td, "out.orbr")
+        refio.write_frames(fin, frames)
+        cmd = [demo, "run", fin, fout, str(p["nfeatures"]), repr(float(p["scale"])), str(p["nlevels"]), str(p["ini"]),
+               str(p["mn"]), str(p["lap"][0]), str(p["lap"][1]), "1" if dump else "0", mode]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stderr)
+        return refio.read_results(fout), r.stderr
+
+
+def test_cpp_class_fails_loudly_without_gpu(demo, images):
+    """No CPU fallback: without a CUDA device operator() returns -1 and reports why."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    p = dict(nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 0))
+    res, err = run_demo(demo, images["luna"], p, dump=False)
+    assert res[0]["ret"] == -1 and len(res[0]["kps"]) == 0
+    assert "no CUDA device" in err or "CUDA" in err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,mode", [("luna_1000_mono", "six"), ("robot866_1000_lap", "six"), ("tum_room4_1500", "six"),
+                                       ("robot866_1000_mono", "five"), ("robot2196_1200_stereo", "threads"),
+                                       ("luna_500_5lv_s15", "six")])
+def test_cpp_class_matches_reference(demo, images, case, mode):
+    g = load_golden(case)
+    p = g["params"]
+    res, _ = run_demo(demo, images[g["image_name"]], p, mode=mode)
+    r = res[0]
+    assert r["ret"] == int(g["ret"])
+    ref = g["kps"]
+    assert len(r["kps"]) == len(ref)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(r["kps"][f], ref[f]), f
+    assert np.max(np.abs(r["kps"]["angle"] - ref["angle"]), initial=0.0) <= 1e-3
+    assert desc_bit_agreement(r["desc"], g["desc"]) >= 0.999
+    import zlib
+    for l in range(p["nlevels"]):
+        assert zlib.crc32(r["pyr"][l].tobytes()) == int(g["pyr_crc"][l])          # mvImagePyramid incl. border
+        assert len(r["level_kps"][l]) == int(g["counts"][l])                       # allLevelsKeypoints / ComputeKeyPointsOctTree
+        for f in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(r["level_kps"][l][f], g["level_kps"][l][f])
+
+
+@pytest.mark.gpu
+def test_cpp_class_multiple_frames_and_empty(demo, images):
+    frames = np.stack([images["robot866"], np.full((480, 640), 77, np.uint8), images["robot2196"]])
+    p = dict(nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 1000))
+    res, _ = run_demo(demo, frames, p, dump=False)
+    g = load_golden("robot866_1000_mono")
+    assert kp_bytes_equal(res[0]["kps"][["x", "y", "size", "response", "octave", "class_id"]],
+                          g["kps"][["x", "y", "size", "response", "octave", "class_id"]])
+    assert res[1]["ret"] == 0 and len(res[1]["kps"]) == 0                            # flat frame: descriptors released
+    assert len(res[2]["kps"]) > 500
