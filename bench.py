@@ -71,40 +71,51 @@ def make_frames(n_frames, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (one looping nvidia-smi
+    process, 50 ms period; only samples taken between __enter__ and __exit__ are kept)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.index, self.rows, self._p = index, [], None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                        "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._p.stdout.readline()          # first sample = the loop is running before the timed region starts
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=10)
+        if self._p is None:
+            return
+        time.sleep(0.06)
+        self._p.terminate()
+        try:
+            out, _ = self._p.communicate(timeout=5)
+        except Exception:
+            self._p.kill()
+            out = ""
+        for line in out.splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 7:
+                self.rows.append(c)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if num(r[1]) is not None]
+        pw = [num(r[2]) for r in self.rows if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 def cpu_reference_run(frames_np, seconds, threads):
@@ -166,7 +177,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=4096, help="frames per step and per GPU")
