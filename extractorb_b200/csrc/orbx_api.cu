@@ -37,6 +37,7 @@ struct PlanEntry {
     int2* d_xtab = nullptr;
     int2* d_ytab = nullptr;
     OrbxCell* d_cells = nullptr;
+    uint8_t* d_slot_level = nullptr;
     long long pyr_stride = 0, blur_stride = 0, cand_stride = 0;
     size_t fast_smem = 0, qt_smem = 0;
     int max_cells_dim = 0;
@@ -70,6 +71,8 @@ struct OrbxHandle {
     int ws_frames = 0;
     OrbxWs ws{};
     int8_t* d_pattern = nullptr;
+    float* d_pattern_f = nullptr;
+    int2* d_angle_w = nullptr;
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
     void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
@@ -163,7 +166,7 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
 
 void free_plan(PlanEntry* p) {
     if (!p) return;
-    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells);
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_slot_level);
     delete p;
 }
 
@@ -296,6 +299,13 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     if (!pe->xtab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_xtab, pe->xtab.data(), pe->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->ytab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_ytab, pe->ytab.data(), pe->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->cells.empty()) ORBX_CUDA(cudaMemcpy(pe->d_cells, pe->cells.data(), pe->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint8_t> sl((size_t)std::max(P.kp_total, 1), 0);
+        for (int l = 0; l < L; ++l)
+            for (int i = 0; i < P.lv[l].kp_cap; ++i) sl[(size_t)P.lv[l].kp_off + i] = (uint8_t)l;
+        ORBX_CUDA(cudaMalloc(&pe->d_slot_level, sl.size()));
+        ORBX_CUDA(cudaMemcpy(pe->d_slot_level, sl.data(), sl.size(), cudaMemcpyHostToDevice));
+    }
     *out = pe;
     return ORBX_OK;
 }
@@ -325,6 +335,7 @@ int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
     w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.pattern = h->d_pattern;
+    w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.slot_level = pe->d_slot_level;
     h->ws_plan = pe; h->ws_frames = frames;
     return ORBX_OK;
 }
@@ -509,6 +520,33 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern, sizeof(kPatternHost));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice);
+    {
+        std::vector<float> pf(1024);
+        // device layout [k][lane][4]: test t = 8*lane + k (descriptor byte `lane`, bit k) so that a warp's loads coalesce
+        for (int t = 0; t < 256; ++t)
+            for (int c = 0; c < 4; ++c) pf[(size_t)((t & 7) * 32 + (t >> 3)) * 4 + c] = (float)kPatternHost[4 * t + c];
+        // IC_Angle weight words: byte k of the aligned row window is patch column u = k - al - 15 (:82-97)
+        std::vector<int2> aw((size_t)4 * 31 * ORBX_ANGLE_WORDS);
+        for (int al = 0; al < 4; ++al)
+            for (int row = 0; row < 31; ++row)
+                for (int wd = 0; wd < ORBX_ANGLE_WORDS; ++wd) {
+                    unsigned wu = 0, wm = 0;
+                    const int v = row - ORBX_HALF_PATCH;
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const int uu = 4 * wd + bb - al - ORBX_HALF_PATCH;
+                        const int au = uu < 0 ? -uu : uu;
+                        if (au <= ORBX_HALF_PATCH && au <= h->umax[v < 0 ? -v : v]) {
+                            wu |= (unsigned)(uu & 0xff) << (8 * bb);
+                            wm |= 1u << (8 * bb);
+                        }
+                    }
+                    aw[((size_t)al * 31 + row) * ORBX_ANGLE_WORDS + wd] = make_int2((int)wu, (int)wm);
+                }
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern_f, pf.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern_f, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_angle_w, aw.size() * sizeof(int2));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_angle_w, aw.data(), aw.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { delete h; return ORBX_ERR_CUDA; }
     *out = h;
     return ORBX_OK;
@@ -520,7 +558,7 @@ void orbx_destroy(OrbxHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_plans(h);
     free_plan(h->dist_plan);
-    cudaFree(h->d_pattern); cudaFree(h->d_in); cudaFree(h->d_out);
+    cudaFree(h->d_pattern); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);

@@ -825,54 +825,76 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbxFloa
 }
 
 #define ORBX_DESC_WARPS 8
+#define ORBX_ANGLE_WORDS 9   // 31 patch columns + up to 3 bytes of alignment slack = 9 aligned words per row
+
+__device__ __forceinline__ int dp4a_u8_s8(unsigned a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// cvRound for |v| < 2^22 without F2I: adding 1.5*2^23 rounds to nearest-even at integer granularity; the
+// integer is the low mantissa bits (bias removed by the caller).
+#define ORBX_RND_MAGIC 12582912.0f
+#define ORBX_RND_BIAS 0x4B400000
 
 __global__ void __launch_bounds__(ORBX_DESC_WARPS * 32)
 k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFloatConsts fc,
            void* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
            int cap_per_frame, int32_t* __restrict__ counts, int frame_out0) {
+    __shared__ __align__(16) uint8_t s_patch[ORBX_DESC_WARPS][37 * 44 + 4];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * ORBX_DESC_WARPS + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
+    if (slot >= plan.kp_total) return;
+    // ---- per-frame level prefix {keypoints, lapping keypoints} by warp scan ----
     const int2* lc = ws.level_count + frame * plan.nlevels;
-    // level of this slot + totals
-    int level = -1, idx = 0, n_before = 0, lap_before = 0, n_total = 0, lap_total = 0;
-    for (int l = 0; l < plan.nlevels; ++l) {
-        const int2 c = lc[l];
-        const int off = plan.lv[l].kp_off;
-        if (slot >= off && slot < off + plan.lv[l].kp_cap) {
-            level = l; idx = slot - off; n_before = n_total; lap_before = lap_total;
-        }
-        n_total += c.x; lap_total += c.y;
+    int2 mine = make_int2(0, 0);
+    if (lane < plan.nlevels) mine = lc[lane];
+    int incn = mine.x, incl = mine.y;
+#pragma unroll
+    for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) {
+        const int tn = __shfl_up_sync(ORBX_FULL_MASK, incn, o), tl = __shfl_up_sync(ORBX_FULL_MASK, incl, o);
+        if (lane >= o) { incn += tn; incl += tl; }
     }
+    const int n_total = __shfl_sync(ORBX_FULL_MASK, incn, ORBX_MAX_LEVELS - 1);
+    const int lap_total = __shfl_sync(ORBX_FULL_MASK, incl, ORBX_MAX_LEVELS - 1);
     const long long fo = (long long)(frame_out0 + frame);
     if (slot == 0 && lane == 0 && counts) {
         counts[2 * fo] = n_total;
         counts[2 * fo + 1] = n_total - lap_total;  // monoIndex, the reference's return value (:1161)
     }
-    if (level < 0 || idx >= lc[level].x) return;
+    const int level = ws.slot_level[slot];
+    const int n_level = __shfl_sync(ORBX_FULL_MASK, mine.x, level);
+    const int n_before = __shfl_sync(ORBX_FULL_MASK, incn - mine.x, level);
+    const int lap_before = __shfl_sync(ORBX_FULL_MASK, incl - mine.y, level);
     const OrbxLevel& L = plan.lv[level];
+    const int idx = slot - L.kp_off;
+    if (idx >= n_level) return;
     OrbxKpRec* recp = ws.kprec + (long long)frame * ws.kp_stride + L.kp_off + idx;
     const OrbxKpRec rec = *recp;
-    const int cx = __float2int_rn(rec.x), cy = __float2int_rn(rec.y);
+    const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
-    // ---- IC_Angle on the un-blurred level ----
+    // ---- IC_Angle on the un-blurred level: 31 rows x 9 aligned words, IDP.4A against per-alignment
+    // weight words (u inside the circle, else 0) and mask words (1 inside the circle) ----
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    const uint8_t* ctr = plane + (long long)(ORBX_EDGE + cy) * L.pitch + ORBX_PADL + cx;
+    const int col0 = ORBX_PADL + cx - ORBX_HALF_PATCH;
+    const int al = col0 & 3;
+    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + cy - ORBX_HALF_PATCH) * L.pitch + (col0 - al));
+    const int2* wt = ws.angle_w + al * (31 * ORBX_ANGLE_WORDS);
+    const int pw = L.pitch >> 2;
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - ORBX_HALF_PATCH;
-        const int au = u < 0 ? -u : u;
-        int colsum = 0;
 #pragma unroll
-        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= plan.umax[av]) {
-                const int val = ctr[(long long)v * L.pitch + u];
-                colsum += val;
-                m01 += v * val;
-            }
+    for (int it = 0; it < (31 * ORBX_ANGLE_WORDS + 31) / 32; ++it) {
+        const int i = it * 32 + lane;
+        if (i < 31 * ORBX_ANGLE_WORDS) {
+            const int row = (i * 57) >> 9;                 // i / 9 for i < 288
+            const int wd = i - row * ORBX_ANGLE_WORDS;
+            const unsigned px = __ldg(p32 + row * pw + wd);
+            const int2 w = __ldg(wt + i);
+            m10 = dp4a_u8_s8(px, w.x, m10);
+            m01 += (row - ORBX_HALF_PATCH) * (int)__dp4a(px, (unsigned)w.y, 0u);
         }
-        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -883,22 +905,41 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
 
     // ---- rBRIEF on the blurred level: lane i computes descriptor byte i ----
     const float rad = __fmul_rn(angle, fc.deg2rad);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-    const uint8_t* bl = ws.blur + (long long)frame * ws.blur_stride + L.blur_off + (long long)cy * L.blur_pitch + cx;
-    const int4* pat = reinterpret_cast<const int4*>(ws.pattern) + lane * 2;
-    const int4 p0 = __ldg(pat), p1 = __ldg(pat + 1);
-    const int pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    // FP32 sincosf (<= 2 ulp).  The reference calls glibc cosf/sinf (:111); a 1-ulp difference in a or b moves a
+    // rounded sample coordinate with probability < 1e-6, and FP64 sincos is ~10x slower here.
+    float a, b;
+    sincosf(rad, &b, &a);
+    // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory with aligned,
+    // coalesced 32-bit loads, then gather the 512 samples from there.
+    const int bp = L.blur_pitch;
+    const int bx0 = cx - 18, o0 = bx0 & 3;
+    const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
+                                                              (long long)(cy - 18) * bp + (bx0 - o0));
+    uint8_t* patch = s_patch[threadIdx.x >> 5];
+    const int bpw = bp >> 2;
+#pragma unroll
+    for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
+        const int i = it * 32 + lane;
+        if (i < 37 * 11) {
+            const int row = (i * 373) >> 12;               // i / 11 for i < 407
+            const int wd = i - row * 11;
+            reinterpret_cast<uint32_t*>(patch)[i] = __ldg(b32 + row * bpw + wd);
+        }
+    }
+    __syncwarp();
+    // sample index = (round(r)+18)*44 + round(c)+18+o0; the rounding bias of both terms is folded into K
+    const int K = (18 - ORBX_RND_BIAS) * 44 + (18 + o0 - ORBX_RND_BIAS);
+    const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)(int)(signed char)(pw[k] & 0xff), y0 = (float)(int)(signed char)((pw[k] >> 8) & 0xff);
-        const float x1 = (float)(int)(signed char)((pw[k] >> 16) & 0xff), y1 = (float)(int)(signed char)((pw[k] >> 24) & 0xff);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bl[(long long)r0 * L.blur_pitch + c0];
-        const int t1 = bl[(long long)r1 * L.blur_pitch + c1];
+        const float4 t = __ldg(pat + k * 32);   // test 8*lane + k: x0, y0, x1, y1
+        const float r0 = __fadd_rn(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)), ORBX_RND_MAGIC);
+        const float c0 = __fadd_rn(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)), ORBX_RND_MAGIC);
+        const float r1 = __fadd_rn(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)), ORBX_RND_MAGIC);
+        const float c1 = __fadd_rn(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)), ORBX_RND_MAGIC);
+        const int t0 = patch[__float_as_int(r0) * 44 + __float_as_int(c0) + K];
+        const int t1 = patch[__float_as_int(r1) * 44 + __float_as_int(c1) + K];
         val |= (t0 < t1) << k;
     }
 

@@ -91,6 +91,9 @@ struct OrbxWs {
     const int2* ytab;
     const OrbxCell* cells;
     const int8_t* pattern; // 256 x 4 int8
+    const float* pattern_f;   // the same as floats (x0, y0, x1, y1 per test)
+    const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
+    const uint8_t* slot_level; // kept-keypoint slot -> level
 };
 
 #endif
