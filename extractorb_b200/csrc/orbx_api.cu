@@ -283,7 +283,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     pe->pyr_stride = align_up(plane_off, 256);
     pe->blur_stride = align_up(blur_off, 256);
     pe->cand_stride = align_up(cand_off, 4);
-    pe->fast_smem = (size_t)ORBX_FAST_WARPS * (2 * (size_t)P.fast_tp * P.fast_trows + 2 * (size_t)P.fast_qcap);
+    pe->fast_smem = (size_t)ORBX_FAST_WARPS * (size_t)align_up(2 * align_up((long long)P.fast_tp * P.fast_trows, 16) + 2ll * P.fast_qcap, 16);
     pe->qt_smem = (size_t)qt_nc * 64;
     if (pe->qt_smem > 200 * 1024 || qt_nc > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "nfeatures per level too large for the quadtree kernel's shared memory"); }
     if (pe->fast_smem > 200 * 1024) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }

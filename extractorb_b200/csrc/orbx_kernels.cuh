@@ -12,6 +12,7 @@
 #ifndef ORBX_KERNELS_CUH_
 #define ORBX_KERNELS_CUH_
 
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -249,36 +250,33 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const OrbxLevel& L = plan.lv[cell.level];
 
     const int tp = plan.fast_tp;
-    const int tile_bytes = tp * plan.fast_trows;
-    uint8_t* tile = smem_fast + (size_t)wib * (2 * tile_bytes + 2 * plan.fast_qcap);
+    const int tile_bytes = (tp * plan.fast_trows + 15) & ~15;            // 16-byte aligned sub-buffers
+    uint8_t* tile = smem_fast + (size_t)wib * ((2 * tile_bytes + 2 * plan.fast_qcap + 15) & ~15);
     uint8_t* score = tile + tile_bytes;
     uint16_t* queue = reinterpret_cast<uint16_t*>(score + tile_bytes);
 
     const int cw = cell.cw, ch = cell.ch;
-    // ---- stage the cell image (aligned 32-bit loads; pixel (r,c) lands at tile[r*tp + a + c]) ----
+    // ---- stage the cell image (aligned 32-bit cp.async; pixel (r,c) lands at tile[r*tp + a + c]) while the
+    // score map is cleared with 128-bit stores ----
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int gx = ORBX_PADL + cell.x0;
     const int a = gx & 3;
     const int nwords = (a + cw + 3) >> 2;
-    const uint8_t* g0 = plane + (long long)(ORBX_EDGE + cell.y0) * L.pitch + (gx - a);
     {
-        const int rows_per_it = 32 / nwords;
-        if (rows_per_it >= 1) {
-            const int lr = lane / nwords, lw = lane - lr * nwords;
-            if (lr < rows_per_it)
-                for (int r = lr; r < ch; r += rows_per_it) {
-                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(g0 + (long long)r * L.pitch) + lw);
-                    *reinterpret_cast<uint32_t*>(tile + r * tp + 4 * lw) = v;
-                }
-        } else {
-            for (int r = 0; r < ch; ++r)
-                for (int wd = lane; wd < nwords; wd += 32) {
-                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(g0 + (long long)r * L.pitch) + wd);
-                    *reinterpret_cast<uint32_t*>(tile + r * tp + 4 * wd) = v;
-                }
+        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + cell.y0) * L.pitch + (gx - a));
+        const int pw = L.pitch >> 2, tpw4 = tp >> 2;
+        const int total = nwords * ch;                                   // < 2^13
+        const unsigned wmagic = (1u << 20) / (unsigned)nwords + 1u;      // i / nwords == (i * wmagic) >> 20
+        for (int i = lane; i < total; i += 32) {
+            const int r = (int)(((unsigned)i * wmagic) >> 20);
+            const int wd = i - r * nwords;
+            __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(tile) + r * tpw4 + wd, g32 + r * pw + wd, 4);
         }
+        __pipeline_commit();
+        const int nz = (ch * tp + 15) >> 4;
+        for (int i = lane; i < nz; i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+        __pipeline_wait_prior(0);
     }
-    for (int i = lane; i < (tile_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
     __syncwarp();
 
     const int ih = ch - 6;
@@ -287,6 +285,9 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int ngrp = ((a + cw - 4) >> 2) - wq0 + 1;
     const int ngroups = ngrp * ih;
     const unsigned gmagic = (1u << 24) / (unsigned)ngrp + 1u;  // idx / ngrp == (idx * gmagic) >> 24 (idx < 2^13)
+    const int wq_last = wq0 + ngrp - 1;
+    const unsigned first_mask = (0xFu << ((a + 3) & 3)) & 0xFu;               // interior starts at byte a+3
+    const unsigned last_mask = 0xFu >> (3 - ((a + cw - 4) & 3));              // interior ends at byte a+cw-4
     // The reference detects at iniThFAST and re-runs the cell at minThFAST only if that found nothing
     // (:818-838); the same two phases here, the second one skipped when it cannot add anything.
     int qn = 0, n_out = 0, use_th = plan.ini_th;
@@ -329,21 +330,24 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
                         const unsigned zz = (z1 | z2) & 0x80008000u;
                         z |= ((zz >> 15) & 1u) << (2 * hlf) | ((zz >> 31) & 1u) << (2 * hlf + 1);
                     }
-                    // keep only interior pixels of this word
-                    const int b0 = 4 * wq;
-                    unsigned valid = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) valid |= (unsigned)(b0 + j >= a + 3 && b0 + j < a + cw - 3) << j;
-                    m4 = z & valid;
-                    pbase = (gr + 3) * tp + b0;
+                    // keep only interior pixels of this word (only a row's first / last word is partial)
+                    m4 = z & (wq == wq0 ? first_mask : 0xFu) & (wq == wq_last ? last_mask : 0xFu);
+                    pbase = (gr + 3) * tp + 4 * wq;
                 }
+                // queue slots by warp prefix sum of the per-lane counts (queue order is irrelevant: every entry
+                // carries its own position)
+                const int cnt = __popc(m4);
+                int inc = cnt;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool pass = (m4 >> j) & 1u;
-                    const unsigned bal = __ballot_sync(ORBX_FULL_MASK, pass);
-                    if (pass) queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pbase + j);
-                    qn += __popc(bal);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t_ = __shfl_up_sync(ORBX_FULL_MASK, inc, o);
+                    if (lane >= o) inc += t_;
                 }
+                int pos = qn + inc - cnt;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((m4 >> j) & 1u) queue[pos++] = (uint16_t)(pbase + j);
+                qn += __shfl_sync(ORBX_FULL_MASK, inc, 31);
             }
         }
         __syncwarp();
@@ -364,8 +368,9 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
                 const int p = queue[e];
                 if (p != 0xffff) {
                     const int s = score[p];
-                    lm = s > score[p - 1] && s > score[p + 1] && s > score[p - tp - 1] && s > score[p - tp] &&
-                         s > score[p - tp + 1] && s > score[p + tp - 1] && s > score[p + tp] && s > score[p + tp + 1];
+                    const int nb = max(max(max((int)score[p - 1], (int)score[p + 1]), max((int)score[p - tp - 1], (int)score[p - tp])),
+                                       max(max((int)score[p - tp + 1], (int)score[p + tp - 1]), max((int)score[p + tp], (int)score[p + tp + 1])));
+                    lm = s > nb;
                     if (!lm) queue[e] = 0xffff;
                 }
             }
@@ -875,6 +880,25 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     const OrbxKpRec rec = *recp;
     const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
+    // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory with aligned
+    // 32-bit cp.async copies, issued first so that they overlap the moment computation below.
+    const int bp = L.blur_pitch;
+    const int bx0 = cx - 18, o0 = bx0 & 3;
+    const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
+                                                              (long long)(cy - 18) * bp + (bx0 - o0));
+    uint8_t* patch = s_patch[threadIdx.x >> 5];
+    const int bpw = bp >> 2;
+#pragma unroll
+    for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
+        const int i = it * 32 + lane;
+        if (i < 37 * 11) {
+            const int row = (i * 373) >> 12;               // i / 11 for i < 407
+            const int wd = i - row * 11;
+            __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(patch) + i, b32 + row * bpw + wd, 4);
+        }
+    }
+    __pipeline_commit();
+
     // ---- IC_Angle on the un-blurred level: 31 rows x 9 aligned words, IDP.4A against per-alignment
     // weight words (u inside the circle, else 0) and mask words (1 inside the circle) ----
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
@@ -909,23 +933,7 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     // rounded sample coordinate with probability < 1e-6, and FP64 sincos is ~10x slower here.
     float a, b;
     sincosf(rad, &b, &a);
-    // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory with aligned,
-    // coalesced 32-bit loads, then gather the 512 samples from there.
-    const int bp = L.blur_pitch;
-    const int bx0 = cx - 18, o0 = bx0 & 3;
-    const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
-                                                              (long long)(cy - 18) * bp + (bx0 - o0));
-    uint8_t* patch = s_patch[threadIdx.x >> 5];
-    const int bpw = bp >> 2;
-#pragma unroll
-    for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
-        const int i = it * 32 + lane;
-        if (i < 37 * 11) {
-            const int row = (i * 373) >> 12;               // i / 11 for i < 407
-            const int wd = i - row * 11;
-            reinterpret_cast<uint32_t*>(patch)[i] = __ldg(b32 + row * bpw + wd);
-        }
-    }
+    __pipeline_wait_prior(0);
     __syncwarp();
     // sample index = (round(r)+18)*44 + round(c)+18+o0; the rounding bias of both terms is folded into K
     const int K = (18 - ORBX_RND_BIAS) * 44 + (18 + o0 - ORBX_RND_BIAS);
