@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <cstdint>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -217,7 +218,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
             }
             pe->rs_rows[l] = rows;
-            pe->rs_pitch[l] = (int)align_up(cols + 3 + 3, 4);
+            pe->rs_pitch[l] = (int)align_up(cols + 15 + 15, 16);     // 16-byte aligned window start + whole 16-byte vectors
             const int pw = V.pitch / 4, rw0 = (ORBX_PADL + V.w) / 4;
             pe->border_items = std::max(pe->border_items, 2 * ORBX_EDGE * pw + V.h * (ORBX_PADL / 4 + pw - rw0));
         }
@@ -381,18 +382,21 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     }
     int64_t launches = 0;
     if (stages & STAGES_PYRAMID) {
-        const dim3 blk(64, 4);
         {
             const OrbxLevel& V = P.lv[0];
-            const dim3 grd((V.pitch / 4 + 63) / 64, (V.plane_rows + 3) / 4, nf);
-            k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride);
+            const dim3 blk(32, 8);
+            const dim3 grd((V.pitch / 16 + 31) / 32, (V.plane_rows + 7) / 8, nf);
+            const int aligned16 = ((uintptr_t)d_imgs % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0) ? 1 : 0;
+            k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride, aligned16);
             ++launches;
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const OrbxLevel& V = P.lv[l];
             const dim3 grd((V.w + ORBX_RS_TW - 1) / ORBX_RS_TW, (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nf);
-            const size_t smem = align_up((long long)pe->rs_rows[l] * pe->rs_pitch[l], 16) + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2;
-            k_pyr_resize<<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
+            const size_t smem = (size_t)pe->rs_rows[l] * pe->rs_pitch[l] + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2;
+            const bool area = pe->xtab[V.xtab_off].y == -1;
+            if (area) k_pyr_resize<true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
+            else k_pyr_resize<false><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
             ++launches;
         }
         if (P.nlevels > 1) {
@@ -455,10 +459,12 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
         ORBX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
     size_t rs = 0;
     for (int l = 1; l < pe->plan.nlevels; ++l)
-        rs = std::max(rs, (size_t)align_up((long long)pe->rs_rows[l] * pe->rs_pitch[l], 16) + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2);
+        rs = std::max(rs, (size_t)pe->rs_rows[l] * pe->rs_pitch[l] + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2);
     if (rs > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "scale factor too large for the resize kernel's shared memory");
-    if (rs > 48 * 1024)
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    if (rs > 48 * 1024) {
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    }
     return ORBX_OK;
 }
 

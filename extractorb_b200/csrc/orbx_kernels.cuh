@@ -26,43 +26,58 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 // =================================================================================================
-// K1  ComputePyramid.  One thread produces one aligned 32-bit word (4 pixels) of the bordered plane,
-// border included: a border pixel is the level pixel at the reflect-101 coordinate, so it is simply
-// recomputed there (no second pass, no dependency on neighbouring CTAs).
+// K1  ComputePyramid.
 // =================================================================================================
+// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213).  One thread produces 16 bytes of the bordered
+// plane: interior chunks are one 128-bit load + store when the source row is 16-byte aligned, everything else
+// (border, unaligned input) is assembled byte by byte from the reflected coordinate.
 __global__ void __launch_bounds__(256)
 k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8_t* __restrict__ imgs,
-             long long row_stride, long long frame_stride) {
+             long long row_stride, long long frame_stride, int aligned16) {
     const OrbxLevel& L = plan.lv[0];
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte chunk index within a row
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
     const int frame = blockIdx.z;
-    if (wx * 4 >= L.pitch || r >= L.plane_rows) return;
+    if (cx * 16 >= L.pitch || r >= L.plane_rows) return;
     const uint8_t* src = imgs + (long long)frame * frame_stride;
     const int y = reflect101(r - ORBX_EDGE, L.h);
     const uint8_t* srow = src + (long long)y * row_stride;
-    uint32_t word = 0;
+    const int dx0 = cx * 16 - ORBX_PADL;
+    uint4 out;
+    if (aligned16 && dx0 >= 0 && dx0 + 16 <= L.w) {
+        out = __ldg(reinterpret_cast<const uint4*>(srow + dx0));
+    } else {
+        uint32_t wv[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int dx = wx * 4 + b - ORBX_PADL;
-        uint32_t v = 0;
-        if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = __ldg(srow + reflect101(dx, L.w));
-        word |= v << (8 * b);
+        for (int q = 0; q < 4; ++q) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int dx = dx0 + 4 * q + b;
+                uint32_t v = 0;
+                if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = __ldg(srow + reflect101(dx, L.w));
+                word |= v << (8 * b);
+            }
+            wv[q] = word;
+        }
+        out = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
     uint8_t* dst = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch + wx * 4) = word;
+    *reinterpret_cast<uint4*>(dst + (long long)r * L.pitch + cx * 16) = out;
 }
 
 // cv::resize INTER_LINEAR, 8UC1 fixed point (11-bit coefficients), the model pinned in oracle/cv_prims.c:
 //   H(y', x) = S[y'][sx]*a0 + S[y'][sx+1]*a1                      (int32, coefficients x2048)
 //   dst(y,x) = ( ((b0*(H(sy,x)>>4))>>16) + ((b1*(H(sy+1,x)>>4))>>16) + 2 ) >> 2
-// Separable and staged through shared memory: a CTA owns a 128x16 tile of the level (ROI only), stages
-// the source rows/columns it needs with aligned 32-bit loads, runs the horizontal pass once per staged
-// source row (H>>4 fits 16 bits) and the vertical pass from shared memory, and stores aligned words.
+// Separable and staged through shared memory: a CTA owns a 128x64 tile of the level (ROI only), stages the
+// source window with 16-byte cp.async, runs the horizontal pass once per staged source row (H>>4 fits 16
+// bits) and the vertical pass from shared memory (IMAD.HI against b<<16), and stores aligned words.
 // Borders are filled afterwards by k_pyr_border (level l+1 never reads level l's border: edge taps clamp).
+// AREA: exact 2x2 decimation, where OpenCV switches INTER_LINEAR to the INTER_AREA fast path.
 #define ORBX_RS_TW 128
-#define ORBX_RS_TH 16
+#define ORBX_RS_TH 64
 
+template <bool AREA>
 __global__ void __launch_bounds__(256)
 k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_s) {
     extern __shared__ __align__(16) uint8_t smem_rs[];
@@ -81,71 +96,74 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y_last]).x + 1, S.h - 1);
     const int nrows = sy_hi - sy_lo + 1;
     const int gcol = ORBX_PADL + sx_lo;            // plane byte column of the first staged pixel
-    const int al = gcol & 3;
-    const int nwords = (al + (sx_hi - sx_lo + 1) + 3) >> 2;
+    const int al = gcol & 15;
+    const int nvec = (al + (sx_hi - sx_lo + 1) + 15) >> 4;
     uint8_t* s_src = smem_rs;                                           // [src_rows_max][src_pitch_s]
-    uint16_t* s_h = reinterpret_cast<uint16_t*>(smem_rs + (((size_t)src_rows_max * src_pitch_s + 15) & ~(size_t)15));  // [src_rows_max][TW]
-    // ---- stage ----
+    uint16_t* s_h = reinterpret_cast<uint16_t*>(smem_rs + (size_t)src_rows_max * src_pitch_s);  // [src_rows_max][TW]
+    // ---- stage (16-byte cp.async; plane rows are 64-byte aligned) ----
     {
-        const uint32_t* g = reinterpret_cast<const uint32_t*>(splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al));
-        const int pw = S.pitch >> 2, spw = src_pitch_s >> 2;
-        const int total = nrows * nwords;
-        const unsigned wmagic = (1u << 20) / (unsigned)nwords + 1u;     // i / nwords for i < 2^12
+        const uint8_t* g = splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al);
+        const int total = nrows * nvec;
+        const unsigned vmagic = (1u << 20) / (unsigned)nvec + 1u;       // i / nvec for i < 2^12
         for (int i = tid; i < total; i += 256) {
-            const int r = (int)(((unsigned)i * wmagic) >> 20);
-            const int wd = i - r * nwords;
-            reinterpret_cast<uint32_t*>(s_src)[r * spw + wd] = __ldg(g + r * pw + wd);
+            const int r = (int)(((unsigned)i * vmagic) >> 20);
+            const int v = i - r * nvec;
+            __pipeline_memcpy_async(s_src + r * src_pitch_s + 16 * v, g + (long long)r * S.pitch + 16 * v, 16);
         }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
     }
     __syncthreads();
-    const bool area = __ldg(&xtab[x0]).y == -1;    // exact 2x2 decimation: OpenCV takes the INTER_AREA fast path
-    // ---- horizontal pass: thread owns one destination column ----
+    // ---- horizontal pass: thread owns one destination column, walks the staged rows ----
     {
         const int c = tid & (ORBX_RS_TW - 1);
-        const int2 xt = __ldg(&xtab[min(x0 + c, L.w - 1)]);
-        const int so = xt.x - sx_lo + al;
-        const int so1 = min(xt.x + 1, S.w - 1) - sx_lo + al;
-        const int a0 = xt.y & 0xffff, a1 = (xt.y >> 16) & 0xffff;
-        for (int r = tid >> 7; r < nrows; r += 2) {
-            const uint8_t* row = s_src + r * src_pitch_s;
-            const int v = area ? (row[so] + row[so1]) : ((row[so] * a0 + row[so1] * a1) >> 4);
-            s_h[r * ORBX_RS_TW + c] = (uint16_t)v;
+        if (x0 + c <= x_last) {
+            const int2 xt = __ldg(&xtab[x0 + c]);
+            const uint8_t* p0 = s_src + (xt.x - sx_lo + al);
+            const uint8_t* p1 = s_src + (min(xt.x + 1, S.w - 1) - sx_lo + al);
+            const int a0 = xt.y & 0xffff, a1 = (xt.y >> 16) & 0xffff;
+            uint16_t* hp = s_h + c;
+#pragma unroll 4
+            for (int r = tid >> 7; r < nrows; r += 2) {
+                const int u0 = p0[r * src_pitch_s], u1 = p1[r * src_pitch_s];
+                hp[r * ORBX_RS_TW] = (uint16_t)(AREA ? (u0 + u1) : ((u0 * a0 + u1 * a1) >> 4));
+            }
         }
     }
     __syncthreads();
-    // ---- vertical pass: 4 columns x 1 row per item, one aligned word per store ----
+    // ---- vertical pass: warp w owns rows w, w+8, ...; lane owns 4 columns (one aligned word) ----
     uint8_t* droi = fbase + L.plane_off + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int x = x0 + 4 * lane;
+    if (x <= x_last) {
+        for (int y = y0 + wrp; y <= y_last; y += 8) {
+            const int2 yt = __ldg(&ytab[y]);
+            const int r0 = yt.x - sy_lo, r1 = min(yt.x + 1, S.h - 1) - sy_lo;
+            const unsigned b0 = (unsigned)(yt.y & 0xffff) << 16, b1 = (unsigned)(yt.y >> 16) << 16;
+            const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + r0 * ORBX_RS_TW + 4 * lane);
+            const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + r1 * ORBX_RS_TW + 4 * lane);
+            const unsigned p0[4] = {h0.x & 0xffffu, h0.x >> 16, h0.y & 0xffffu, h0.y >> 16};
+            const unsigned p1[4] = {h1.x & 0xffffu, h1.x >> 16, h1.y & 0xffffu, h1.y >> 16};
+            uint32_t word = 0;
 #pragma unroll
-    for (int it = 0; it < (ORBX_RS_TW / 4) * ORBX_RS_TH / 256; ++it) {
-        const int item = tid + it * 256;
-        const int cg = item & 31, ry = item >> 5;
-        const int x = x0 + 4 * cg, y = y0 + ry;
-        if (y > y_last || x > x_last) continue;
-        const int2 yt = __ldg(&ytab[y]);
-        const int r0 = yt.x - sy_lo, r1 = min(yt.x + 1, S.h - 1) - sy_lo;
-        const int b0 = yt.y & 0xffff, b1 = (yt.y >> 16) & 0xffff;
-        const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + r0 * ORBX_RS_TW + 4 * cg);
-        const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + r1 * ORBX_RS_TW + 4 * cg);
-        const int p0[4] = {(int)(h0.x & 0xffff), (int)(h0.x >> 16), (int)(h0.y & 0xffff), (int)(h0.y >> 16)};
-        const int p1[4] = {(int)(h1.x & 0xffff), (int)(h1.x >> 16), (int)(h1.y & 0xffff), (int)(h1.y >> 16)};
-        uint32_t word = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = area ? ((p0[j] + p1[j] + 2) >> 2) : ((((b0 * p0[j]) >> 16) + ((b1 * p1[j]) >> 16) + 2) >> 2);
-            word |= (uint32_t)(v & 0xff) << (8 * j);
-        }
-        uint8_t* d = droi + (long long)y * L.pitch + x;
-        if (x + 3 <= x_last) {
-            *reinterpret_cast<uint32_t*>(d) = word;
-        } else {
-            for (int j = 0; x + j <= x_last; ++j) d[j] = (uint8_t)(word >> (8 * j));
+            for (int j = 0; j < 4; ++j) {
+                const unsigned v = AREA ? ((p0[j] + p1[j] + 2) >> 2) : ((__umulhi(p0[j], b0) + __umulhi(p1[j], b1) + 2) >> 2);
+                word |= (v & 0xffu) << (8 * j);
+            }
+            uint8_t* d = droi + (long long)y * L.pitch + x;
+            if (x + 3 <= x_last) {
+                *reinterpret_cast<uint32_t*>(d) = word;
+            } else {
+                for (int j = 0; x + j <= x_last; ++j) d[j] = (uint8_t)(word >> (8 * j));
+            }
         }
     }
 }
 
-// copyMakeBorder(BORDER_REFLECT_101) of levels >= 1 (:1193): one thread per aligned word of the border
-// frame (top/bottom bands and the left/right strips); a border pixel is the level pixel at the reflected
-// coordinate.  Level 0's border is written by k_pyr_level0.
+// copyMakeBorder(BORDER_REFLECT_101) of levels >= 1 (:1193).  Work items are aligned words: the top/bottom
+// bands (38 rows, copied word-wise from the reflected row where the word lies inside the level, assembled
+// byte-wise at the corners) and the left/right strips of the middle rows (byte-wise).  Level 0's border is
+// written by k_pyr_level0.
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int level = blockIdx.y + 1;
@@ -169,15 +187,19 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
         wx = q < (ORBX_PADL >> 2) ? q : rw0 + (q - (ORBX_PADL >> 2));
     }
     uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    const uint8_t* roi = plane + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
-    const uint8_t* srow = roi + (long long)reflect101(r - ORBX_EDGE, L.h) * L.pitch;
+    const uint8_t* srow = plane + (long long)(ORBX_EDGE + reflect101(r - ORBX_EDGE, L.h)) * L.pitch + ORBX_PADL;
+    const int dx0 = wx * 4 - ORBX_PADL;
     uint32_t word = 0;
+    if (dx0 >= 0 && dx0 + 4 <= L.w) {
+        word = *reinterpret_cast<const uint32_t*>(srow + dx0);
+    } else {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int dx = wx * 4 + b - ORBX_PADL;
-        uint32_t v = 0;
-        if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = srow[reflect101(dx, L.w)];
-        word |= v << (8 * b);
+        for (int b = 0; b < 4; ++b) {
+            const int dx = dx0 + b;
+            uint32_t v = 0;
+            if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = srow[reflect101(dx, L.w)];
+            word |= v << (8 * b);
+        }
     }
     *reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch + wx * 4) = word;
 }
