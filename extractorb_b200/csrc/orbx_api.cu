@@ -385,7 +385,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
         {
             const OrbxLevel& V = P.lv[0];
             const dim3 blk(32, 8);
-            const dim3 grd((V.pitch / 16 + 31) / 32, (V.plane_rows + 7) / 8, nf);
+            const dim3 grd(((V.w + 15) / 16 + 31) / 32, (V.h + 7) / 8, nf);
             const int aligned16 = ((uintptr_t)d_imgs % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0) ? 1 : 0;
             k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride, aligned16);
             ++launches;
@@ -399,8 +399,10 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
             else k_pyr_resize<false><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
             ++launches;
         }
-        if (P.nlevels > 1) {
-            k_pyr_border<<<dim3((pe->border_items + 255) / 256, P.nlevels - 1, nf), 256, 0, st>>>(P, ws);
+        {
+            int max_rows = 0;
+            for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
+            k_pyr_border<<<dim3((max_rows + 7) / 8, P.nlevels, nf), dim3(32, 8), 0, st>>>(P, ws);
             ++launches;
         }
     }

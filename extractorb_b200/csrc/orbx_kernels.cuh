@@ -28,42 +28,24 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // =================================================================================================
 // K1  ComputePyramid.
 // =================================================================================================
-// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213).  One thread produces 16 bytes of the bordered
-// plane: interior chunks are one 128-bit load + store when the source row is 16-byte aligned, everything else
-// (border, unaligned input) is assembled byte by byte from the reflected coordinate.
+// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213): this kernel copies the image into the level-0
+// ROI (16 bytes per thread; 128-bit loads when the source rows are 16-byte aligned), k_pyr_border then fills
+// the border of every level.
 __global__ void __launch_bounds__(256)
 k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8_t* __restrict__ imgs,
              long long row_stride, long long frame_stride, int aligned16) {
     const OrbxLevel& L = plan.lv[0];
-    const int cx = blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte chunk index within a row
-    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int frame = blockIdx.z;
-    if (cx * 16 >= L.pitch || r >= L.plane_rows) return;
-    const uint8_t* src = imgs + (long long)frame * frame_stride;
-    const int y = reflect101(r - ORBX_EDGE, L.h);
-    const uint8_t* srow = src + (long long)y * row_stride;
-    const int dx0 = cx * 16 - ORBX_PADL;
-    uint4 out;
-    if (aligned16 && dx0 >= 0 && dx0 + 16 <= L.w) {
-        out = __ldg(reinterpret_cast<const uint4*>(srow + dx0));
+    if (x >= L.w || y >= L.h) return;
+    const uint8_t* srow = imgs + (long long)frame * frame_stride + (long long)y * row_stride + x;
+    uint8_t* drow = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + y) * L.pitch + ORBX_PADL + x;
+    if (aligned16 && x + 16 <= L.w) {
+        *reinterpret_cast<uint4*>(drow) = __ldg(reinterpret_cast<const uint4*>(srow));
     } else {
-        uint32_t wv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int dx = dx0 + 4 * q + b;
-                uint32_t v = 0;
-                if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = __ldg(srow + reflect101(dx, L.w));
-                word |= v << (8 * b);
-            }
-            wv[q] = word;
-        }
-        out = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        for (int j = 0; j < 16 && x + j < L.w; ++j) drow[j] = __ldg(srow + j);
     }
-    uint8_t* dst = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    *reinterpret_cast<uint4*>(dst + (long long)r * L.pitch + cx * 16) = out;
 }
 
 // cv::resize INTER_LINEAR, 8UC1 fixed point (11-bit coefficients), the model pinned in oracle/cv_prims.c:
@@ -160,39 +142,34 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     }
 }
 
-// copyMakeBorder(BORDER_REFLECT_101) of levels >= 1 (:1193).  Work items are aligned words: the top/bottom
-// bands (38 rows, copied word-wise from the reflected row where the word lies inside the level, assembled
-// byte-wise at the corners) and the left/right strips of the middle rows (byte-wise).  Level 0's border is
-// written by k_pyr_level0.
+// copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  One thread row (threadIdx.y) per plane
+// row.  Band rows (the 19 rows above / below the level) are whole rows: words inside the level's columns are
+// copied from the reflected row, the rest assembled byte-wise.  Middle rows only have the left/right strips.
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
-    const int level = blockIdx.y + 1;
+    const int level = blockIdx.y;
     const int frame = blockIdx.z;
     const OrbxLevel& L = plan.lv[level];
+    const int r = blockIdx.x * blockDim.y + threadIdx.y;
+    if (r >= L.plane_rows) return;
     const int pw = L.pitch >> 2;
     const int rw0 = (ORBX_PADL + L.w) >> 2;            // first word touching the right border
-    const int nside = (ORBX_PADL >> 2) + (pw - rw0);   // words per middle row: left strip + right strip
-    const int nband = 2 * ORBX_EDGE * pw;              // top + bottom bands
-    const int total = nband + L.h * nside;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int r, wx;
-    if (i < nband) {
-        r = i / pw; wx = i - r * pw;
-        if (r >= ORBX_EDGE) r += L.h;
-    } else {
-        const int k = i - nband;
-        const int rr = k / nside, q = k - rr * nside;
-        r = ORBX_EDGE + rr;
-        wx = q < (ORBX_PADL >> 2) ? q : rw0 + (q - (ORBX_PADL >> 2));
-    }
+    const bool band = r < ORBX_EDGE || r >= ORBX_EDGE + L.h;
     uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const uint8_t* srow = plane + (long long)(ORBX_EDGE + reflect101(r - ORBX_EDGE, L.h)) * L.pitch + ORBX_PADL;
-    const int dx0 = wx * 4 - ORBX_PADL;
-    uint32_t word = 0;
-    if (dx0 >= 0 && dx0 + 4 <= L.w) {
-        word = *reinterpret_cast<const uint32_t*>(srow + dx0);
-    } else {
+    uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch);
+    if (band) {
+        // interior columns: straight word copies
+        const int wfirst = ORBX_PADL >> 2, wlast = ((ORBX_PADL + L.w) >> 2) - 1;   // words fully inside the level
+        for (int wx = wfirst + threadIdx.x; wx <= wlast; wx += blockDim.x)
+            drow[wx] = *reinterpret_cast<const uint32_t*>(srow + (wx * 4 - ORBX_PADL));
+    }
+    // left strip (words 0..7) and right strip (words rw0..pw-1), byte-wise with the reflected column
+    const int nside = (ORBX_PADL >> 2) + (pw - rw0);
+    for (int q = threadIdx.x; q < nside; q += blockDim.x) {
+        const int wx = q < (ORBX_PADL >> 2) ? q : rw0 + (q - (ORBX_PADL >> 2));
+        const int dx0 = wx * 4 - ORBX_PADL;
+        uint32_t word = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int dx = dx0 + b;
@@ -200,8 +177,8 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
             if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = srow[reflect101(dx, L.w)];
             word |= v << (8 * b);
         }
+        drow[wx] = word;
     }
-    *reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch + wx * 4) = word;
 }
 
 // =================================================================================================
@@ -874,6 +851,14 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     const int slot = blockIdx.x * ORBX_DESC_WARPS + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
     if (slot >= plan.kp_total) return;
+    // level of this slot from the plan (no memory access), record load issued together with the level counts
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < ORBX_MAX_LEVELS; ++l) level += (l < plan.nlevels && slot >= plan.lv[l].kp_off) ? 1 : 0;
+    const OrbxLevel& L = plan.lv[level];
+    const int idx = slot - L.kp_off;
+    OrbxKpRec* recp = ws.kprec + (long long)frame * ws.kp_stride + slot;
+    const OrbxKpRec rec = *recp;
     // ---- per-frame level prefix {keypoints, lapping keypoints} by warp scan ----
     const int2* lc = ws.level_count + frame * plan.nlevels;
     int2 mine = make_int2(0, 0);
@@ -891,15 +876,10 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
         counts[2 * fo] = n_total;
         counts[2 * fo + 1] = n_total - lap_total;  // monoIndex, the reference's return value (:1161)
     }
-    const int level = ws.slot_level[slot];
     const int n_level = __shfl_sync(ORBX_FULL_MASK, mine.x, level);
     const int n_before = __shfl_sync(ORBX_FULL_MASK, incn - mine.x, level);
     const int lap_before = __shfl_sync(ORBX_FULL_MASK, incl - mine.y, level);
-    const OrbxLevel& L = plan.lv[level];
-    const int idx = slot - L.kp_off;
     if (idx >= n_level) return;
-    OrbxKpRec* recp = ws.kprec + (long long)frame * ws.kp_stride + L.kp_off + idx;
-    const OrbxKpRec rec = *recp;
     const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
     // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory with aligned
@@ -958,7 +938,7 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     __pipeline_wait_prior(0);
     __syncwarp();
     // sample index = (round(r)+18)*44 + round(c)+18+o0; the rounding bias of both terms is folded into K
-    const int K = (18 - ORBX_RND_BIAS) * 44 + (18 + o0 - ORBX_RND_BIAS);
+    const int K = (int)((unsigned)(18 - ORBX_RND_BIAS) * 44u + (unsigned)(18 + o0 - ORBX_RND_BIAS));   // wraps, like the index arithmetic
     const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
     int val = 0;
 #pragma unroll
