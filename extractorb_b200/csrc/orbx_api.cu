@@ -39,6 +39,7 @@ struct PlanEntry {
     int2* d_ytab = nullptr;
     OrbxCell* d_cells = nullptr;
     uint8_t* d_slot_level = nullptr;
+    uint32_t* d_blur_tiles = nullptr;
     long long pyr_stride = 0, blur_stride = 0, cand_stride = 0;
     size_t fast_smem = 0, qt_smem = 0;
     int max_cells_dim = 0;
@@ -167,7 +168,7 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
 
 void free_plan(PlanEntry* p) {
     if (!p) return;
-    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_slot_level);
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_slot_level); cudaFree(p->d_blur_tiles);
     delete p;
 }
 
@@ -288,10 +289,14 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     pe->qt_smem = (size_t)qt_nc * 64;
     if (pe->qt_smem > 200 * 1024 || qt_nc > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "nfeatures per level too large for the quadtree kernel's shared memory"); }
     if (pe->fast_smem > 200 * 1024) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
-    int tiles = 0;
+    std::vector<uint32_t> btiles;
     for (int l = 0; l < L; ++l)
-        tiles += ((P.lv[l].w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW) * ((P.lv[l].h + ORBX_BLUR_TH - 1) / ORBX_BLUR_TH);
-    pe->blur_tiles = tiles;
+        for (int ty = 0; ty < (P.lv[l].h + ORBX_BLUR_TH - 1) / ORBX_BLUR_TH; ++ty)
+            for (int tx = 0; tx < (P.lv[l].w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; ++tx)
+                btiles.push_back((uint32_t)l | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+    pe->blur_tiles = (int)btiles.size();
+    ORBX_CUDA(cudaMalloc(&pe->d_blur_tiles, btiles.size() * sizeof(uint32_t)));
+    ORBX_CUDA(cudaMemcpy(pe->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     // device tables
     const size_t nx = std::max<size_t>(pe->xtab.size(), 1), ny = std::max<size_t>(pe->ytab.size(), 1);
     ORBX_CUDA(cudaMalloc(&pe->d_xtab, nx * sizeof(int2)));
@@ -336,7 +341,7 @@ int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
     w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.pattern = h->d_pattern;
-    w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.slot_level = pe->d_slot_level;
+    w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.slot_level = pe->d_slot_level; w.blur_tiles = pe->d_blur_tiles;
     h->ws_plan = pe; h->ws_frames = frames;
     return ORBX_OK;
 }

@@ -717,47 +717,46 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // border is exactly the BORDER_REFLECT_101 extension of the borderless clone the reference blurs).
 // =================================================================================================
 #define ORBX_BLUR_TW 128
-#define ORBX_BLUR_TH 32
+#define ORBX_BLUR_TH 64
 
 // Horizontal taps via IDP.4A on byte-aligned windows (funnel shifts of the staged words), vertical taps via
 // IDP.2A on 16-bit horizontal sums stored as row pairs (rows 2k, 2k+1 share one 32-bit word per column).
+// blockIdx.x indexes a host-built tile table (level | tile_x << 8 | tile_y << 20).
 __global__ void __launch_bounds__(256)
 k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
-    constexpr int SROWS = ORBX_BLUR_TH + 6;          // 38 staged rows = 19 row pairs
-    constexpr int SW = (ORBX_BLUR_TW + 8) / 4;       // 34 words per staged row (cols x0-4 .. x0+131)
+    constexpr int SROWS = ORBX_BLUR_TH + 6;          // 70 staged rows = 35 row pairs
+    constexpr int SPB = ORBX_BLUR_TW + 32;           // staged bytes per row: columns x0-16 .. x0+143 (16-byte chunks)
+    constexpr int SW = SPB / 4;
     __shared__ __align__(16) uint32_t s_src[SROWS * SW];
     __shared__ __align__(16) uint32_t s_h2[(SROWS / 2) * ORBX_BLUR_TW];
-    int level = 0, tile = blockIdx.x;
-    for (; level < plan.nlevels; ++level) {
-        const int nt = ((plan.lv[level].w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW) * ((plan.lv[level].h + ORBX_BLUR_TH - 1) / ORBX_BLUR_TH);
-        if (tile < nt) break;
-        tile -= nt;
-    }
-    if (level >= plan.nlevels) return;
+    const uint32_t tdesc = __ldg(ws.blur_tiles + blockIdx.x);
+    const int level = tdesc & 0xff;
     const OrbxLevel& L = plan.lv[level];
     const int frame = blockIdx.y;
     if (ws.level_count[frame * plan.nlevels + level].x == 0) return;  // reference skips empty levels (:1122)
-    const int tiles_x = (L.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW;
-    const int ty = tile / tiles_x;
-    const int x0 = (tile - ty * tiles_x) * ORBX_BLUR_TW, y0 = ty * ORBX_BLUR_TH;
-    const uint32_t* plane = reinterpret_cast<const uint32_t*>(ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off);
+    const int x0 = ((tdesc >> 8) & 0xfff) * ORBX_BLUR_TW, y0 = (tdesc >> 20) * ORBX_BLUR_TH;
+    const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int tid = threadIdx.x;
-    const int pw = L.pitch >> 2, max_word = pw - 1;
-    const int w0 = (ORBX_PADL + x0 - 4) >> 2;
-    for (int i = tid; i < SROWS * SW; i += 256) {
-        const int r = i / SW, wd = i - r * SW;
-        const int pr = min(ORBX_EDGE + y0 + r - 3, L.plane_rows - 1);
-        s_src[i] = __ldg(plane + pr * pw + min(w0 + wd, max_word));
+    {
+        const int max_chunk = (L.pitch >> 4) - 1, c0 = (ORBX_PADL + x0 - 16) >> 4;
+        for (int i = tid; i < SROWS * (SPB / 16); i += 256) {
+            const int r = i / (SPB / 16), c = i - r * (SPB / 16);
+            const int pr = min(ORBX_EDGE + y0 + r - 3, L.plane_rows - 1);
+            __pipeline_memcpy_async(reinterpret_cast<uint8_t*>(s_src) + r * SPB + 16 * c,
+                                    plane + (long long)pr * L.pitch + 16 * min(c0 + c, max_chunk), 16);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
     }
     __syncthreads();
-    // ---- horizontal: item = (row pair, 4-pixel group); output x reads staged bytes x+1 .. x+7 ----
+    // ---- horizontal: item = (row pair, 4-pixel group); output x reads staged bytes x+13 .. x+19 ----
     const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
     for (int i = tid; i < (SROWS / 2) * (ORBX_BLUR_TW / 4); i += 256) {
         const int rp = i >> 5, xq = i & 31;
         uint32_t h[2][4];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const uint32_t* s = s_src + (2 * rp + k) * SW + xq;
+            const uint32_t* s = s_src + (2 * rp + k) * SW + xq + 3;
             const uint32_t a = s[0], b = s[1], c = s[2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

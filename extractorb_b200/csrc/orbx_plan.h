@@ -94,6 +94,7 @@ struct OrbxWs {
     const float* pattern_f;   // the same as floats (x0, y0, x1, y1 per test)
     const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
     const uint8_t* slot_level; // kept-keypoint slot -> level
+    const uint32_t* blur_tiles; // blur tile table: level | tile_x << 8 | tile_y << 20
 };
 
 #endif
