@@ -407,7 +407,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
         {
             int max_rows = 0;
             for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
-            k_pyr_border<<<dim3((max_rows + 7) / 8, P.nlevels, nf), dim3(32, 8), 0, st>>>(P, ws);
+            k_pyr_border<<<dim3((max_rows + 15) / 16, P.nlevels, nf), dim3(16, 16), 0, st>>>(P, ws);
             ++launches;
         }
     }

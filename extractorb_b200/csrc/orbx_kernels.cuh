@@ -142,9 +142,11 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     }
 }
 
-// copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  One thread row (threadIdx.y) per plane
-// row.  Band rows (the 19 rows above / below the level) are whole rows: words inside the level's columns are
-// copied from the reflected row, the rest assembled byte-wise.  Middle rows only have the left/right strips.
+// copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  16 lanes per plane row.  A border word
+// (4 pixels) is a byte-reversed, funnel-shifted window of the level row: for the left strip pixels dx..dx+3
+// (dx < 0) mirror level pixels -dx-3..-dx, for the right strip they mirror 2(w-1)-dx-3..2(w-1)-dx.  The word
+// that straddles level and border keeps its level bytes.  Band rows (the 19 rows above / below the level)
+// additionally copy the level columns from the reflected row.
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int level = blockIdx.y;
@@ -152,30 +154,37 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const OrbxLevel& L = plan.lv[level];
     const int r = blockIdx.x * blockDim.y + threadIdx.y;
     if (r >= L.plane_rows) return;
-    const int pw = L.pitch >> 2;
-    const int rw0 = (ORBX_PADL + L.w) >> 2;            // first word touching the right border
+    const int lane = threadIdx.x;                              // 0..15
     const bool band = r < ORBX_EDGE || r >= ORBX_EDGE + L.h;
     uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    const uint8_t* srow = plane + (long long)(ORBX_EDGE + reflect101(r - ORBX_EDGE, L.h)) * L.pitch + ORBX_PADL;
-    uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch);
+    // level row this plane row mirrors (itself for middle rows), as words relative to level column 0
+    const uint32_t* srow = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + reflect101(r - ORBX_EDGE, L.h)) * L.pitch + ORBX_PADL);
+    uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch + ORBX_PADL);   // word 0 = level column 0
     if (band) {
-        // interior columns: straight word copies
-        const int wfirst = ORBX_PADL >> 2, wlast = ((ORBX_PADL + L.w) >> 2) - 1;   // words fully inside the level
-        for (int wx = wfirst + threadIdx.x; wx <= wlast; wx += blockDim.x)
-            drow[wx] = *reinterpret_cast<const uint32_t*>(srow + (wx * 4 - ORBX_PADL));
+        const int nw = L.w >> 2;                               // words fully inside the level
+        for (int wx = lane; wx < nw; wx += 16) drow[wx] = srow[wx];
     }
-    // left strip (words 0..7) and right strip (words rw0..pw-1), byte-wise with the reflected column
-    const int nside = (ORBX_PADL >> 2) + (pw - rw0);
-    for (int q = threadIdx.x; q < nside; q += blockDim.x) {
-        const int wx = q < (ORBX_PADL >> 2) ? q : rw0 + (q - (ORBX_PADL >> 2));
-        const int dx0 = wx * 4 - ORBX_PADL;
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int dx = dx0 + b;
-            uint32_t v = 0;
-            if (dx >= -ORBX_EDGE && dx < L.w + ORBX_EDGE) v = srow[reflect101(dx, L.w)];
-            word |= v << (8 * b);
+    const int rw0 = L.w >> 2;                                  // first right-strip word (may straddle level/border)
+    const int rwl = (L.w + ORBX_EDGE - 1) >> 2;                // last word holding border pixels
+    const int nright = rwl - rw0 + 1;
+    if (lane < 5) {
+        // left strip: words -5..-1 (pixels -20..-1; pixel -20 is padding)
+        const int wx = lane - 5;
+        const int k = -wx - 1;                                 // level words k, k+1 hold pixels 4k+1 .. 4k+4
+        const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8);
+        drow[wx] = __byte_perm(v, 0, 0x0123);
+    } else if (lane - 5 < nright) {
+        const int wx = rw0 + (lane - 5);
+        const int dx0 = 4 * wx;
+        const int s0 = 2 * (L.w - 1) - dx0 - 3;                // first mirrored level pixel (>= 0 since w > 22)
+        const int k = s0 >> 2;
+        const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8 * (s0 & 3));
+        uint32_t word = __byte_perm(v, 0, 0x0123);
+        const int keep = L.w - dx0;                            // level bytes at the start of a straddling word
+        if (keep > 0) {
+            const uint32_t orig = srow[wx];
+            const uint32_t sel = keep == 1 ? 0x7650u : (keep == 2 ? 0x7610u : 0x7210u);
+            word = __byte_perm(orig, word, sel);
         }
         drow[wx] = word;
     }
