@@ -201,28 +201,33 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // =================================================================================================
 #define ORBX_FAST_WARPS 4
 
+// best(p) with both sides evaluated at once: X_k = (255 + c - v_k) | (255 + v_k - c) << 16 is one IMAD per
+// ring pixel (v_k * 65535 + B; both halves stay in [0, 510], so no borrow crosses the halves), and the
+// max-over-arcs-of-min chain runs on 16-bit SIMD (VIMNMX3.S16x2): low half = "ring darker" side, high half =
+// "ring brighter" side.  Arcs of 9 = min3 of three consecutive min3 triples.
 __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ t, int p, int tp) {
-    const int c = t[p];
-    int d[16];
-    d[0] = c - t[p + 3 * tp];      d[1] = c - t[p + 3 * tp + 1];  d[2] = c - t[p + 2 * tp + 2];
-    d[3] = c - t[p + tp + 3];      d[4] = c - t[p + 3];           d[5] = c - t[p - tp + 3];
-    d[6] = c - t[p - 2 * tp + 2];  d[7] = c - t[p - 3 * tp + 1];  d[8] = c - t[p - 3 * tp];
-    d[9] = c - t[p - 3 * tp - 1];  d[10] = c - t[p - 2 * tp - 2]; d[11] = c - t[p - tp - 3];
-    d[12] = c - t[p - 3];          d[13] = c - t[p + tp - 3];     d[14] = c - t[p + 2 * tp - 2];
-    d[15] = c - t[p + 3 * tp - 1];
-    int mn3[16], mx3[16];
+    const unsigned c = t[p];
+    const unsigned B = 255u + (255u << 16) + c * (1u - 65536u);
+    unsigned x[16];
+    x[0] = t[p + 3 * tp] * 65535u + B;      x[1] = t[p + 3 * tp + 1] * 65535u + B;  x[2] = t[p + 2 * tp + 2] * 65535u + B;
+    x[3] = t[p + tp + 3] * 65535u + B;      x[4] = t[p + 3] * 65535u + B;           x[5] = t[p - tp + 3] * 65535u + B;
+    x[6] = t[p - 2 * tp + 2] * 65535u + B;  x[7] = t[p - 3 * tp + 1] * 65535u + B;  x[8] = t[p - 3 * tp] * 65535u + B;
+    x[9] = t[p - 3 * tp - 1] * 65535u + B;  x[10] = t[p - 2 * tp - 2] * 65535u + B; x[11] = t[p - tp - 3] * 65535u + B;
+    x[12] = t[p - 3] * 65535u + B;          x[13] = t[p + tp - 3] * 65535u + B;     x[14] = t[p + 2 * tp - 2] * 65535u + B;
+    x[15] = t[p + 3 * tp - 1] * 65535u + B;
+    unsigned m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    int bright = -256, dark = 256;
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(x[k], x[(k + 1) & 15], x[(k + 2) & 15]);
+    unsigned m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        bright = max(bright, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-        dark = min(dark, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
-    }
-    return max(bright, -dark);
+    for (int k = 0; k < 16; ++k) m9[k] = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    unsigned r0 = __vimax3_s16x2(m9[0], m9[1], m9[2]), r1 = __vimax3_s16x2(m9[3], m9[4], m9[5]);
+    unsigned r2 = __vimax3_s16x2(m9[6], m9[7], m9[8]), r3 = __vimax3_s16x2(m9[9], m9[10], m9[11]);
+    unsigned r4 = __vimax3_s16x2(m9[12], m9[13], m9[14]);
+    r0 = __vimax3_s16x2(r0, r1, r2);
+    r3 = __vimax3_s16x2(r3, r4, m9[15]);
+    r0 = __vmaxs2(r0, r3);
+    return (int)max(r0 & 0xffffu, r0 >> 16) - 255;
 }
 
 // Upper bound of best(p) from the 8 antipodal ring pairs: every arc of 9 contiguous ring pixels contains
