@@ -510,10 +510,10 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     QtShared q;
     {
         uint8_t* p = smem_qt;
+        q.cc = reinterpret_cast<int*>(p); p += (size_t)NC * 16;      // first: read as int4 (16-byte aligned)
         q.skey = reinterpret_cast<unsigned long long*>(p); p += (size_t)NC * 8;
         q.rect[0] = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;
         q.rect[1] = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;
-        q.cc = reinterpret_cast<int*>(p); p += (size_t)NC * 16;
         q.cnt[0] = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
         q.cnt[1] = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
         q.seq = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
@@ -668,9 +668,9 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
             if (cb >= 0) {
                 const uint32_t v = cand[k].x;
                 const int c = qt_quadrant(rect[pos], (int)(v & CM), (int)((v >> ORBX_COORD_BITS) & CM));
-                int before = 0;
-                for (int j = 0; j < c; ++j) before += q.cc[4 * pos + j] > 0;
-                np = T - 1 - (cb + before);
+                const int4 cc4 = *reinterpret_cast<const int4*>(q.cc + 4 * pos);
+                const unsigned occ = (cc4.x > 0) | ((cc4.y > 0) << 1) | ((cc4.z > 0) << 2) | ((cc4.w > 0) << 3);
+                np = T - 1 - (cb + __popc(occ & ((1u << c) - 1u)));
             } else {
                 np = T + q.surv[pos];
             }
@@ -855,7 +855,7 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned a, int b, int c) {
 #define ORBX_RND_MAGIC 12582912.0f
 #define ORBX_RND_BIAS 0x4B400000
 
-__global__ void __launch_bounds__(ORBX_DESC_WARPS * 32)
+__global__ void __launch_bounds__(ORBX_DESC_WARPS * 32, 8)
 k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFloatConsts fc,
            void* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
            int cap_per_frame, int32_t* __restrict__ counts, int frame_out0) {
