@@ -96,6 +96,10 @@ def test_fixture_stages_vs_oracle(gpu, oracle, images, name):
     (1241, 376, 2000, 8, (0, 0)),         # C4 KITTI
     (1241, 376, 2000, 8, (300, 900)),
     (100, 90, 200, 3, (0, 1000)),         # small image, few levels
+    (641, 479, 1000, 8, (0, 0)),          # odd sizes: partial words / tiles on every level
+    (333, 217, 700, 6, (0, 400)),
+    (1023, 767, 3000, 8, (0, 0)),
+    (130, 128, 150, 4, (0, 0)),           # last level 75x74: a single 30-px cell column/row
     (97, 211, 300, 2, (0, 0)),            # portrait, aspect < 1 (nIni rounds to 1... 0.46 -> error below)
 ])
 def test_synthetic_vs_oracle(gpu, oracle, w, h, nf, nl, lap):
@@ -107,6 +111,28 @@ def test_synthetic_vs_oracle(gpu, oracle, w, h, nf, nl, lap):
         ext.close()
         return
     check_against_oracle(gpu, oracle, img, nf=nf, nl=nl, lap=lap)
+
+
+@pytest.mark.parametrize("scale,nl,ini,mn", [(1.5, 5, 25, 10), (2.0, 3, 20, 7), (1.1, 10, 15, 5), (1.2, 8, 7, 20)])
+def test_other_scales_and_thresholds(gpu, oracle, scale, nl, ini, mn):
+    """scale 2.0 exercises OpenCV's exact-2x INTER_AREA path; (7, 20) has minThFAST > iniThFAST."""
+    img = synth_frame(77, 640, 480)
+    check_against_oracle(gpu, oracle, img, nf=1200, scale=scale, nl=nl, ini=ini, mn=mn)
+
+
+def test_cell_size_35(gpu, oracle):
+    """BASELINE.json's north_star quotes a 35-pixel cell grid; the reference uses W = 30 (ORBextractor.cc:777).
+    The cell size is a parameter on both sides: check W = 35 as well."""
+    img = synth_frame(78, 640, 480)
+    o = oracle.OracleExtractor(1000, 1.2, 8, 20, 7, cell_w=35)
+    oret, okps, odesc = o.extract(img, (0, 0))
+    g = gpu.ORBextractor(1000, 1.2, 8, 20, 7, cell_size=35)
+    gret, gkps, gdesc = g(img, None, (0, 0))
+    assert gret == oret and kp_bytes_equal(gkps[["x", "y", "size", "response", "octave", "class_id"]],
+                                           okps[["x", "y", "size", "response", "octave", "class_id"]])
+    assert np.max(np.abs(gkps["angle"] - okps["angle"]), initial=0.0) <= ANGLE_TOL_DEG
+    assert desc_bit_agreement(gdesc, odesc) >= DESC_BIT_MIN
+    g.close()
 
 
 def test_4k_12_levels(gpu, oracle):
