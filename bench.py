@@ -50,12 +50,28 @@ def stage_algorithmic_bytes(mean_candidates):
     }
 
 
-def make_frames(n_frames, seed):
-    """Deterministic synthetic frame set: N_BASE corner-rich base frames (tests/common.synth_frame), each
-    output frame a cyclic shift / flip / +-20 % gain of one of them.  uint8 torch tensor on the CPU."""
+def natural_base():
+    """The reference's own fixture images (decoded copies in tests/golden/images.npz): two 640x480 robot frames
+    and 640x480 centre crops of the 2x-upsampled 512x512 luna / TUM frames."""
+    with np.load(os.path.join(ROOT, "tests", "golden", "images.npz")) as z:
+        imgs = [z["robot866"], z["robot2196"]]
+        for k in ("luna", "tum_room4"):
+            up = np.kron(z[k], np.ones((2, 2), np.uint8))
+            imgs.append(up[272:272 + H, 192:192 + W])
+    return np.stack(imgs)
+
+
+def make_frames(n_frames, seed, dataset="synthetic"):
+    """Deterministic frame set: base frames (N_BASE corner-rich synthetic frames from tests/common.synth_frame,
+    or the natural fixture images), each output frame a cyclic shift / flip / +-20 % gain of one of them.
+    uint8 torch tensor on the CPU."""
     import torch
     from common import synth_frame
-    base = torch.from_numpy(np.stack([synth_frame(seed * 1000 + i, W, H) for i in range(N_BASE)]))
+    if dataset == "natural":
+        base = torch.from_numpy(natural_base())
+    else:
+        base = torch.from_numpy(np.stack([synth_frame(seed * 1000 + i, W, H) for i in range(N_BASE)]))
+    nb = base.shape[0]
     g = torch.Generator().manual_seed(1234 + seed)
     dy = torch.randint(0, H, (n_frames,), generator=g).tolist()
     dx = torch.randint(0, W, (n_frames,), generator=g).tolist()
@@ -63,7 +79,7 @@ def make_frames(n_frames, seed):
     gain = (0.8 + 0.4 * torch.rand(n_frames, generator=g)).tolist()
     out = torch.empty((n_frames, H, W), dtype=torch.uint8)
     for i in range(n_frames):
-        f = torch.roll(base[i % N_BASE], (dy[i], dx[i]), (0, 1))
+        f = torch.roll(base[i % nb], (dy[i], dx[i]), (0, 1))
         if flip[i]:
             f = torch.flip(f, (1,))
         out[i] = (f.float() * gain[i]).clamp_(0, 255).to(torch.uint8)
@@ -185,6 +201,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-iters", type=int, default=300)
+    ap.add_argument("--no-natural", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -238,6 +256,7 @@ def main():
     ms = e0.elapsed_time(e1)
     stage_ms, _ = ext.stage_times()
     launches = ext.launch_count() - launches0
+    ncand = sum(len(ext.level_candidates(l, frame=0)[0]) for l in range(NLEVELS))   # of one frame of the workload
     counts = d_counts.cpu().numpy()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     kp_sum = torch.tensor([float(counts[:, 0].sum())], dtype=torch.float64, device="cuda")
@@ -270,12 +289,52 @@ def main():
     assert np.array_equal(h_counts.numpy(), counts), "host and device paths disagree"
     ext.stage_times()
 
+    # ---- the same device-resident measurement on the natural-image set (fewer candidates per frame) ----
+    natural = None
+    if world == 1 and not args.no_natural:
+        nat = make_frames(F, seed=7, dataset="natural").cuda()
+        def step_nat():
+            ext.extract_batch_raw(nat.data_ptr(), ex.MEM_DEVICE, F, W, H, W, W * H, (0, 0), d_kps.data_ptr(), d_desc.data_ptr(),
+                                  cap, d_counts.data_ptr(), ex.MEM_DEVICE, stream.cuda_stream)
+        for _ in range(3):
+            step_nat()
+        torch.cuda.synchronize()
+        ext.stage_times()
+        n0, n1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for _ in range(5):
+            step_nat()
+        n1e.record(stream)
+        torch.cuda.synchronize()
+        nat_ms = n0.elapsed_time(n1e)
+        nat_stage, _ = ext.stage_times()
+        natural = {"value": F * 5 / (nat_ms * 1e-3), "unit": "frames/s", "mean_keypoints_per_frame": float(d_counts[:, 0].float().mean().item()),
+                   "stage_ms_per_step": {k: v / 5 for k, v in nat_stage.items()},
+                   "what": "4 natural fixture images (robot x2, luna, TUM room4) with the same shift/flip/gain augmentation, device-resident"}
+        del nat
+
+    # ---- single-frame latency (the reference's own calling pattern: one operator() per frame, host to host) ----
+    lat = None
+    if rank == 0:
+        one = ex.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=1)
+        f0 = host_frames[0].numpy()
+        k1 = np.zeros(cap, ex.KP_DTYPE)
+        d1 = np.zeros((cap, 32), np.uint8)
+        import ctypes as C
+        n1, m1 = C.c_int(0), C.c_int(0)
+        ts = []
+        for i in range(args.latency_iters + 50):
+            t0 = time.perf_counter()
+            one._check(one._L.orbx_extract(one._h, f0.ctypes.data, W, H, W, 0, 0, k1.ctypes.data, d1.ctypes.data, cap,
+                                           C.byref(n1), C.byref(m1)))
+            ts.append((time.perf_counter() - t0) * 1e6)
+        ts = np.array(ts[50:])
+        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "iters": int(len(ts)),
+               "what": "orbx_extract on one 640x480 host frame, host buffers in and out, wall clock"}
+        one.close()
+
     if rank == 0:
         mean_kp = float(kp_sum.item()) / (F * world)
-        # candidates per frame (for the algorithmic byte counts): read back from the resident group
-        ncand = 0
-        for l in range(NLEVELS):
-            ncand += len(ext.level_candidates(l, frame=0)[0])
         alg = stage_algorithmic_bytes(ncand)
         groups_per_step = (F + args.group - 1) // args.group
         n_group_launches = groups_per_step * args.steps
@@ -291,6 +350,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+        traffic, pipe = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/, 256-frame launch)
+            cap_ = json.load(open(os.path.join(ROOT, "profiles", "ncu_capture.json")))[dom]
+            traffic = cap_["dram_bytes_per_launch"] * frames_per_launch / cap_["frames_per_launch"]
+            pipe = cap_.get("pipes")
+        except Exception:
+            pass
         per_rank_fps = value / world
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -301,8 +367,10 @@ def main():
                        "sharding": "independent frames per rank, no data collective (NCCL: timing/statistics all-reduce only)",
                        "mean_keypoints_per_frame": mean_kp, "fast_candidates_frame0": ncand},
             "p50_us_per_frame_amortised": 1e6 / per_rank_fps,
+            "single_frame_latency": lat,
+            "natural_set": natural,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "traffic": traffic, "pipes_from_ncu": pipe, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_frame": alg[dom], "ms_per_launch": dom_ms_per_launch,
                          "frames_per_launch": frames_per_launch,
                          "path": {"algorithmic_bytes_per_frame": PATH_BYTES_PER_FRAME, "achieved": PATH_BYTES_PER_FRAME * per_rank_fps / 1e9,
