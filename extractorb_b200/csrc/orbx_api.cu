@@ -47,6 +47,17 @@ struct PlanEntry {
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
     int border_items = 0;                   // max over levels >= 1 of the border kernel's work items
+    // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
+    struct GraphKey {
+        const void* imgs; long long rs, fs; int nf, lap0, lap1; void* kps; void* desc; int cap; void* counts; int fo, stages;
+        bool operator==(const GraphKey& o) const {
+            return imgs == o.imgs && rs == o.rs && fs == o.fs && nf == o.nf && lap0 == o.lap0 && lap1 == o.lap1 && kps == o.kps &&
+                   desc == o.desc && cap == o.cap && counts == o.counts && fo == o.fo && stages == o.stages;
+        }
+    };
+    struct GraphSlot { GraphKey key; cudaGraphExec_t exec = nullptr; };
+    GraphSlot graphs[4];
+    int graph_next = 0;
 };
 
 struct StageEvents { cudaEvent_t ev[ORBX_NUM_STAGES + 1]; };
@@ -78,6 +89,7 @@ struct OrbxHandle {
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
     void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
+    int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // profiling
     std::vector<StageEvents> events;
@@ -168,6 +180,7 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
 
 void free_plan(PlanEntry* p) {
     if (!p) return;
+    for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_slot_level); cudaFree(p->d_blur_tiles);
     delete p;
 }
@@ -317,6 +330,9 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
 }
 
 void free_workspace(OrbxHandle* h) {
+    for (auto& kv : h->plans)      // captured graphs hold workspace pointers
+        for (auto& g : kv.second->graphs)
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     cudaFree(h->ws.pyr); cudaFree(h->ws.blur); cudaFree(h->ws.cand); cudaFree(h->ws.keynode);
     cudaFree(h->ws.kprec); cudaFree(h->ws.cand_count); cudaFree(h->ws.level_count); cudaFree(h->ws.flags);
     memset(&h->ws, 0, sizeof(h->ws));
@@ -368,13 +384,13 @@ enum { STAGES_PYRAMID = 1, STAGES_KEYPOINTS = 2, STAGES_ALL = 3 };
 
 // Launch the stages for `nf` device-resident frames.  Outputs (device pointers, may be NULL) are written
 // at frame index frame_out0 + f.
-int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
-                 long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
-                 int32_t* d_counts, int frame_out0, int stages) {
+int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
+                     long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
+                     int32_t* d_counts, int frame_out0, int stages, bool in_capture) {
     OrbxPlan P = pe->plan;
     P.lap0 = lap0; P.lap1 = lap1;
     const OrbxWs& ws = h->ws;
-    const bool prof = (h->prm.flags & ORBX_FLAG_PROFILE) != 0;
+    const bool prof = (h->prm.flags & ORBX_FLAG_PROFILE) != 0 && !in_capture;
     StageEvents* se = nullptr;
     if (prof) {
         if (h->events_used == h->events.size()) {
@@ -417,7 +433,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
         k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
-        k_octree<<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);
+        k_octree<<<dim3(P.nlevels, nf), nf <= 8 ? ORBX_QT_THREADS : 256, pe->qt_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
         k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws);
@@ -430,11 +446,50 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     } else if (se) {
         for (int i = 2; i <= ORBX_NUM_STAGES; ++i) ORBX_CUDA(cudaEventRecord(se->ev[i], st));
     }
-    ORBX_CUDA(cudaGetLastError());
+    if (!in_capture) ORBX_CUDA(cudaGetLastError());
     h->stage_launches += launches;
     h->total_launches += launches;
     h->cur = pe;
     h->resident_frames = nf;
+    return ORBX_OK;
+}
+
+// Small launch groups are launch-latency bound (a single frame is 13 dependent kernels): replay them as one
+// CUDA graph, captured once per argument set.  Large groups and profiled runs launch directly.
+int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
+                 long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
+                 int32_t* d_counts, int frame_out0, int stages) {
+    const bool use_graph = nf <= 8 && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_NO_GRAPH);
+    if (!use_graph)
+        return launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
+                                frame_out0, stages, false);
+    const PlanEntry::GraphKey key{d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts, frame_out0, stages};
+    for (auto& g : pe->graphs)
+        if (g.exec && g.key == key) {
+            ORBX_CUDA(cudaGraphLaunch(g.exec, st));
+            const int64_t n = (stages & STAGES_PYRAMID ? pe->plan.nlevels + 1 : 0) + (stages & STAGES_KEYPOINTS ? 4 : 0);
+            h->stage_launches += n; h->total_launches += n;
+            h->cur = pe; h->resident_frames = nf;
+            return ORBX_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    ORBX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
+                              frame_out0, stages, true);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != ORBX_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc != ORBX_OK ? rc : fail(h, ORBX_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    }
+    PlanEntry::GraphSlot& slot = pe->graphs[pe->graph_next];
+    pe->graph_next = (pe->graph_next + 1) % 4;
+    if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    ce = cudaGraphInstantiate(&slot.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { slot.exec = nullptr; return fail(h, ORBX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    slot.key = key;
+    ORBX_CUDA(cudaGraphLaunch(slot.exec, st));
     return ORBX_OK;
 }
 
@@ -475,10 +530,14 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
     return ORBX_OK;
 }
 
-// Did any frame since the last check overflow its candidate workspace?  (Reads and clears the flag word.)
+// Did any frame since the last check overflow its candidate workspace?  The flag word is fetched into pinned
+// memory by fetch_overflow (queued on the compute stream before its final synchronize) and cleared when set.
+int fetch_overflow(OrbxHandle* h, cudaStream_t st) {
+    ORBX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return ORBX_OK;
+}
 int check_overflow(OrbxHandle* h, bool* overflow) {
-    int flag = 0;
-    ORBX_CUDA(cudaMemcpy(&flag, h->ws.flags, sizeof(int), cudaMemcpyDeviceToHost));
+    const int flag = *h->h_flag;
     *overflow = (flag & 1) != 0;
     if (flag) ORBX_CUDA(cudaMemset(h->ws.flags, 0, sizeof(int)));
     return ORBX_OK;
@@ -524,6 +583,7 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     build_ctor_tables(h);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -578,6 +638,7 @@ void orbx_destroy(OrbxHandle* h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
     }
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -674,6 +735,8 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                 ORBX_CUDA(cudaEventRecord(h->ev_done[slot], st));
             }
         }
+        rc = fetch_overflow(h, st);
+        if (rc != ORBX_OK) return rc;
         ORBX_CUDA(cudaStreamSynchronize(st));
         if (host_out) ORBX_CUDA(cudaStreamSynchronize(h->s_out));
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
@@ -724,6 +787,8 @@ static int run_stages_single(OrbxHandle* h, const uint8_t* image, int width, int
     if (rc != ORBX_OK) return rc;
     for (int attempt = 0;; ++attempt) {
         rc = launch_group(h, pe, h->stream, h->d_in, width, (long long)width * height, 1, 0, 0, nullptr, nullptr, 0, nullptr, 0, stages);
+        if (rc != ORBX_OK) return rc;
+        rc = fetch_overflow(h, h->stream);
         if (rc != ORBX_OK) return rc;
         ORBX_CUDA(cudaStreamSynchronize(h->stream));
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }

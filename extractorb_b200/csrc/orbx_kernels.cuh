@@ -436,7 +436,7 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // Keys never move: each key carries the list position of its node and the split geometry is
 // recomputed from the node rectangle.
 // =================================================================================================
-#define ORBX_QT_THREADS 256
+#define ORBX_QT_THREADS 512   // upper bound; large launch groups use 256 (throughput), small ones 512 (latency)
 
 struct QtShared {
     short4* rect[2];  // x0, x1, y0, y1

@@ -55,6 +55,7 @@ typedef struct OrbxParams {
 } OrbxParams;
 
 #define ORBX_FLAG_PROFILE 1 /* record CUDA-event time per stage (orbx_stage_times) */
+#define ORBX_FLAG_NO_GRAPH 2 /* never replay small launch groups as CUDA graphs */
 
 /* Same 28-byte layout as cv::KeyPoint. */
 typedef struct OrbxKeyPoint {
