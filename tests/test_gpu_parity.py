@@ -156,6 +156,40 @@ def test_noise_and_flat_images(gpu, oracle):
     check_against_oracle(gpu, oracle, low, nf=500, nl=4)
 
 
+def test_candidate_workspace_regrowth(gpu, oracle):
+    """A deliberately tiny FAST-candidate workspace must overflow, regrow and still give the exact result
+    (single-frame and batched), never a silently truncated candidate list."""
+    rng = np.random.default_rng(11)
+    noise = rng.integers(0, 256, (240, 320), dtype=np.uint8)
+    o = oracle.OracleExtractor(500, 1.2, 4, 20, 7)
+    oret, okps, odesc = o.extract(noise, (0, 0))
+    g = gpu.ORBextractor(500, 1.2, 4, 20, 7, cand_per_cell=1)
+    gret, gkps, gdesc = g(noise, None, (0, 0))
+    assert gret == oret and kp_bytes_equal(gkps[["x", "y", "response", "octave"]], okps[["x", "y", "response", "octave"]])
+    assert desc_bit_agreement(gdesc, odesc) >= DESC_BIT_MIN
+    g.close()
+    frames = np.stack([noise, synth_frame(5, 320, 240), noise[::-1].copy()])
+    gb = gpu.ORBextractor(500, 1.2, 4, 20, 7, cand_per_cell=1, max_batch=2)
+    counts, kps, desc = gb.extract_batch_host(frames, (0, 0))
+    for f in range(3):
+        r, k, d = o.extract(frames[f], (0, 0))
+        assert counts[f, 0] == len(k) and np.array_equal(kps[f, :len(k)]["x"], k["x"]) and np.array_equal(kps[f, :len(k)]["y"], k["y"])
+    gb.close()
+
+
+def test_large_feature_counts(gpu, oracle):
+    """nfeatures = 5 * 1500 as the reference demos use (main_orb_extractor.cpp:43) and 14 000; beyond ~14.7 k
+    (more than 3 190 features on one level) the quadtree node table no longer fits shared memory: clean error."""
+    img = synth_frame(21, 752, 480)
+    for nf in (7500, 14000):
+        check_against_oracle(gpu, oracle, img, nf=nf, nl=8, lap=(0, 0), stages=False)
+    ext = gpu.ORBextractor(20000, 1.2, 8, 20, 7)
+    with pytest.raises(gpu.OrbxError) as ei:
+        ext(img, None, (0, 0))
+    assert ei.value.code == -2
+    ext.close()
+
+
 def test_checkerboard_ties(gpu, oracle):
     """Equal responses everywhere: exercises first-wins tie-breaking and the equal-size node order."""
     yy, xx = np.mgrid[0:300, 0:400]
