@@ -38,15 +38,12 @@ struct PlanEntry {
     int2* d_xtab = nullptr;
     int2* d_ytab = nullptr;
     OrbxCell* d_cells = nullptr;
-    uint8_t* d_slot_level = nullptr;
     uint32_t* d_blur_tiles = nullptr;
     long long pyr_stride = 0, blur_stride = 0, cand_stride = 0;
     size_t fast_smem = 0, qt_smem = 0;
-    int max_cells_dim = 0;
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
-    int border_items = 0;                   // max over levels >= 1 of the border kernel's work items
     // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
     struct GraphKey {
         const void* imgs; long long rs, fs; int nf, lap0, lap1; void* kps; void* desc; int cap; void* counts; int fo, stages;
@@ -83,7 +80,6 @@ struct OrbxHandle {
     PlanEntry* ws_plan = nullptr;
     int ws_frames = 0;
     OrbxWs ws{};
-    int8_t* d_pattern = nullptr;
     float* d_pattern_f = nullptr;
     int2* d_angle_w = nullptr;
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
@@ -97,8 +93,6 @@ struct OrbxHandle {
     double stage_ms[ORBX_NUM_STAGES] = {0, 0, 0, 0, 0};
     int64_t stage_launches = 0;
     int64_t total_launches = 0;
-    // standalone DistributeOctTree scratch
-    PlanEntry* dist_plan = nullptr;
 };
 
 namespace {
@@ -181,7 +175,7 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
 void free_plan(PlanEntry* p) {
     if (!p) return;
     for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_slot_level); cudaFree(p->d_blur_tiles);
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_blur_tiles);
     delete p;
 }
 
@@ -233,8 +227,6 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
             }
             pe->rs_rows[l] = rows;
             pe->rs_pitch[l] = (int)align_up(cols + 15 + 15, 16);     // 16-byte aligned window start + whole 16-byte vectors
-            const int pw = V.pitch / 4, rw0 = (ORBX_PADL + V.w) / 4;
-            pe->border_items = std::max(pe->border_items, 2 * ORBX_EDGE * pw + V.h * (ORBX_PADL / 4 + pw - rw0));
         }
         // FAST cell grid, :781-814
         const int minBX = ORBX_FAST_BORDER, minBY = ORBX_FAST_BORDER;
@@ -318,13 +310,6 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     if (!pe->xtab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_xtab, pe->xtab.data(), pe->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->ytab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_ytab, pe->ytab.data(), pe->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->cells.empty()) ORBX_CUDA(cudaMemcpy(pe->d_cells, pe->cells.data(), pe->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
-    {
-        std::vector<uint8_t> sl((size_t)std::max(P.kp_total, 1), 0);
-        for (int l = 0; l < L; ++l)
-            for (int i = 0; i < P.lv[l].kp_cap; ++i) sl[(size_t)P.lv[l].kp_off + i] = (uint8_t)l;
-        ORBX_CUDA(cudaMalloc(&pe->d_slot_level, sl.size()));
-        ORBX_CUDA(cudaMemcpy(pe->d_slot_level, sl.data(), sl.size(), cudaMemcpyHostToDevice));
-    }
     *out = pe;
     return ORBX_OK;
 }
@@ -356,8 +341,8 @@ int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
     ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
-    w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.pattern = h->d_pattern;
-    w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.slot_level = pe->d_slot_level; w.blur_tiles = pe->d_blur_tiles;
+    w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells;
+    w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.blur_tiles = pe->d_blur_tiles;
     h->ws_plan = pe; h->ws_frames = frames;
     return ORBX_OK;
 }
@@ -433,7 +418,8 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
-        k_octree<<<dim3(P.nlevels, nf), nf <= 8 ? ORBX_QT_THREADS : 256, pe->qt_smem, st>>>(P, ws);
+        if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws);
+        else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
         k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws);
@@ -517,8 +503,10 @@ int ensure_bytes(OrbxHandle* h, void** p, size_t* have, size_t need, bool pinned
 int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
     if (pe->fast_smem > 48 * 1024)
         ORBX_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->fast_smem));
-    if (pe->qt_smem > 48 * 1024)
-        ORBX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+    if (pe->qt_smem > 48 * 1024) {
+        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+    }
     size_t rs = 0;
     for (int l = 1; l < pe->plan.nlevels; ++l)
         rs = std::max(rs, (size_t)pe->rs_rows[l] * pe->rs_pitch[l] + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2);
@@ -591,8 +579,6 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern, sizeof(kPatternHost));
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice);
     {
         std::vector<float> pf(1024);
         // device layout [k][lane][4]: test t = 8*lane + k (descriptor byte `lane`, bit k) so that a warp's loads coalesce
@@ -630,8 +616,7 @@ void orbx_destroy(OrbxHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_plans(h);
-    free_plan(h->dist_plan);
-    cudaFree(h->d_pattern); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
+    cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -856,8 +841,8 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     ORBX_CUDA_L(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc;
     w.cand_stride = (long long)cand.size(); w.kp_stride = V.kp_cap;
-    if (smem > 48 * 1024) ORBX_CUDA_L(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_octree<<<dim3(1, 1), ORBX_QT_THREADS, smem, h->stream>>>(P, w);
+    if (smem > 48 * 1024) ORBX_CUDA_L(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_octree<ORBX_QT_THREADS_LAT><<<dim3(1, 1), ORBX_QT_THREADS_LAT, smem, h->stream>>>(P, w);
     h->total_launches += 1; h->stage_launches += 1;
     ORBX_CUDA_L(cudaGetLastError());
     int2 lc;

@@ -230,28 +230,6 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ t, int p, i
     return (int)max(r0 & 0xffffu, r0 >> 16) - 255;
 }
 
-// Upper bound of best(p) from the 8 antipodal ring pairs: every arc of 9 contiguous ring pixels contains
-// at least one pixel of each pair, so  best <= max( c - max_pairs(min(a,b)),  min_pairs(max(a,b)) - c ).
-// The first two pairs (vertical, horizontal) reject most pixels of smooth regions after 5 loads.
-__device__ __forceinline__ bool fast_quick(const uint8_t* __restrict__ t, int p, int tp, int th) {
-    const int c = t[p];
-    const int a0 = t[p + 3 * tp], a8 = t[p - 3 * tp], a4 = t[p + 3], a12 = t[p - 3];
-    int dk = max(min(a0, a8), min(a4, a12));   // dark side:   need c - dk > th
-    int br = min(max(a0, a8), max(a4, a12));   // bright side: need br - c > th
-    if (c - dk <= th && br - c <= th) return false;
-    const int a2 = t[p + 2 * tp + 2], a10 = t[p - 2 * tp - 2], a6 = t[p - 2 * tp + 2], a14 = t[p + 2 * tp - 2];
-    dk = __vimax3_s32(dk, min(a2, a10), min(a6, a14));
-    br = __vimin3_s32(br, max(a2, a10), max(a6, a14));
-    if (c - dk <= th && br - c <= th) return false;
-    const int a1 = t[p + 3 * tp + 1], a9 = t[p - 3 * tp - 1], a3 = t[p + tp + 3], a11 = t[p - tp - 3];
-    const int a5 = t[p - tp + 3], a13 = t[p + tp - 3], a7 = t[p - 3 * tp + 1], a15 = t[p + 3 * tp - 1];
-    dk = __vimax3_s32(dk, min(a1, a9), min(a3, a11));
-    br = __vimin3_s32(br, max(a1, a9), max(a3, a11));
-    dk = __vimax3_s32(dk, min(a5, a13), min(a7, a15));
-    br = __vimin3_s32(br, max(a5, a13), max(a7, a15));
-    return c - dk > th || br - c > th;
-}
-
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32)
 k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     extern __shared__ __align__(16) uint8_t smem_fast[];
@@ -436,7 +414,8 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // Keys never move: each key carries the list position of its node and the split geometry is
 // recomputed from the node rectangle.
 // =================================================================================================
-#define ORBX_QT_THREADS 512   // upper bound; large launch groups use 256 (throughput), small ones 512 (latency)
+#define ORBX_QT_THREADS 256      // large launch groups (throughput)
+#define ORBX_QT_THREADS_LAT 512  // small launch groups: one CTA per level is latency bound
 
 struct QtShared {
     short4* rect[2];  // x0, x1, y0, y1
@@ -495,7 +474,8 @@ __device__ int block_excl_scan(int* v, int n, int* scratch) {
     return total;
 }
 
-__global__ void __launch_bounds__(ORBX_QT_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     extern __shared__ __align__(16) uint8_t smem_qt[];
     __shared__ int s_scratch[33];

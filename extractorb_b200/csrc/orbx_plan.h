@@ -90,10 +90,8 @@ struct OrbxWs {
     const int2* xtab;      // resize: {src offset, a0 | a1<<16}
     const int2* ytab;
     const OrbxCell* cells;
-    const int8_t* pattern; // 256 x 4 int8
-    const float* pattern_f;   // the same as floats (x0, y0, x1, y1 per test)
+    const float* pattern_f;   // rBRIEF tests as floats, layout [bit k][descriptor byte][x0, y0, x1, y1]
     const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
-    const uint8_t* slot_level; // kept-keypoint slot -> level
     const uint32_t* blur_tiles; // blur tile table: level | tile_x << 8 | tile_y << 20
 };
 
