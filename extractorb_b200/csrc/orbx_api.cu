@@ -79,7 +79,12 @@ struct OrbxHandle {
     // workspace (sized for ws_frames frames of ws_plan)
     PlanEntry* ws_plan = nullptr;
     int ws_frames = 0;
-    OrbxWs ws{};
+    OrbxWs ws{};                   // workspace set 0 (also the view the accessors read unless res_set == 1)
+    OrbxWs ws2{};                  // workspace set 1: consecutive launch groups alternate sets and compute streams
+    int ws2_frames = 0;
+    int res_set = 0;               // which set holds the resident (last) group
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_s2 = nullptr;
     float* d_pattern_f = nullptr;
     int2* d_angle_w = nullptr;
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
@@ -314,22 +319,24 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     return ORBX_OK;
 }
 
+void free_ws_set(OrbxWs& w, bool own_flags) {
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode);
+    cudaFree(w.kprec); cudaFree(w.cand_count); cudaFree(w.level_count);
+    if (own_flags) cudaFree(w.flags);
+    memset(&w, 0, sizeof(w));
+}
+
 void free_workspace(OrbxHandle* h) {
     for (auto& kv : h->plans)      // captured graphs hold workspace pointers
         for (auto& g : kv.second->graphs)
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    cudaFree(h->ws.pyr); cudaFree(h->ws.blur); cudaFree(h->ws.cand); cudaFree(h->ws.keynode);
-    cudaFree(h->ws.kprec); cudaFree(h->ws.cand_count); cudaFree(h->ws.level_count); cudaFree(h->ws.flags);
-    memset(&h->ws, 0, sizeof(h->ws));
-    h->ws_plan = nullptr; h->ws_frames = 0; h->resident_frames = 0; h->cur = nullptr;
+    free_ws_set(h->ws2, false);
+    free_ws_set(h->ws, true);
+    h->ws_plan = nullptr; h->ws_frames = 0; h->ws2_frames = 0; h->resident_frames = 0; h->cur = nullptr; h->res_set = 0;
 }
 
-int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
-    if (h->ws_plan == pe && h->ws_frames >= frames) return ORBX_OK;
-    ORBX_CUDA(cudaStreamSynchronize(h->stream));
-    free_workspace(h);
+int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* shared_flags) {
     const OrbxPlan& P = pe->plan;
-    OrbxWs& w = h->ws;
     ORBX_CUDA(cudaMalloc(&w.pyr, (size_t)pe->pyr_stride * frames));
     ORBX_CUDA(cudaMalloc(&w.blur, (size_t)pe->blur_stride * frames));
     ORBX_CUDA(cudaMalloc(&w.cand, (size_t)pe->cand_stride * frames * sizeof(uint2)));
@@ -337,13 +344,37 @@ int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames) {
     ORBX_CUDA(cudaMalloc(&w.kprec, (size_t)P.kp_total * frames * sizeof(OrbxKpRec)));
     ORBX_CUDA(cudaMalloc(&w.cand_count, (size_t)P.nlevels * frames * sizeof(int)));
     ORBX_CUDA(cudaMalloc(&w.level_count, (size_t)P.nlevels * frames * sizeof(int2)));
-    ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
-    ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
+    if (shared_flags) {
+        w.flags = shared_flags;
+    } else {
+        ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
+        ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
+    }
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
     w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells;
     w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.blur_tiles = pe->d_blur_tiles;
-    h->ws_plan = pe; h->ws_frames = frames;
+    return ORBX_OK;
+}
+
+// `sets` = 2 allocates the second workspace set used to overlap consecutive launch groups.
+int ensure_workspace(OrbxHandle* h, PlanEntry* pe, int frames, int sets = 1) {
+    if (h->ws_plan != pe || h->ws_frames < frames) {
+        ORBX_CUDA(cudaStreamSynchronize(h->stream));
+        ORBX_CUDA(cudaStreamSynchronize(h->stream2));
+        free_workspace(h);
+        int rc = alloc_ws_set(h, pe, frames, h->ws, nullptr);
+        if (rc != ORBX_OK) return rc;
+        h->ws_plan = pe; h->ws_frames = frames;
+    }
+    if (sets > 1 && h->ws2_frames < frames) {
+        ORBX_CUDA(cudaStreamSynchronize(h->stream2));
+        free_ws_set(h->ws2, false);
+        h->ws2_frames = 0;
+        int rc = alloc_ws_set(h, pe, frames, h->ws2, h->ws.flags);
+        if (rc != ORBX_OK) return rc;
+        h->ws2_frames = frames;
+    }
     return ORBX_OK;
 }
 
@@ -371,10 +402,10 @@ enum { STAGES_PYRAMID = 1, STAGES_KEYPOINTS = 2, STAGES_ALL = 3 };
 // at frame index frame_out0 + f.
 int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
                      long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
-                     int32_t* d_counts, int frame_out0, int stages, bool in_capture) {
+                     int32_t* d_counts, int frame_out0, int stages, bool in_capture, int set = 0) {
     OrbxPlan P = pe->plan;
     P.lap0 = lap0; P.lap1 = lap1;
-    const OrbxWs& ws = h->ws;
+    const OrbxWs& ws = set ? h->ws2 : h->ws;
     const bool prof = (h->prm.flags & ORBX_FLAG_PROFILE) != 0 && !in_capture;
     StageEvents* se = nullptr;
     if (prof) {
@@ -437,6 +468,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
     h->total_launches += launches;
     h->cur = pe;
     h->resident_frames = nf;
+    h->res_set = set;
     return ORBX_OK;
 }
 
@@ -444,18 +476,18 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
 // CUDA graph, captured once per argument set.  Large groups and profiled runs launch directly.
 int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
                  long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
-                 int32_t* d_counts, int frame_out0, int stages) {
-    const bool use_graph = nf <= 8 && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_NO_GRAPH);
+                 int32_t* d_counts, int frame_out0, int stages, int set = 0) {
+    const bool use_graph = set == 0 && nf <= 8 && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_NO_GRAPH);
     if (!use_graph)
         return launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
-                                frame_out0, stages, false);
+                                frame_out0, stages, false, set);
     const PlanEntry::GraphKey key{d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts, frame_out0, stages};
     for (auto& g : pe->graphs)
         if (g.exec && g.key == key) {
             ORBX_CUDA(cudaGraphLaunch(g.exec, st));
             const int64_t n = (stages & STAGES_PYRAMID ? pe->plan.nlevels + 1 : 0) + (stages & STAGES_KEYPOINTS ? 4 : 0);
             h->stage_launches += n; h->total_launches += n;
-            h->cur = pe; h->resident_frames = nf;
+            h->cur = pe; h->resident_frames = nf; h->res_set = 0;
             return ORBX_OK;
         }
     cudaGraph_t graph = nullptr;
@@ -572,6 +604,8 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_s2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -624,6 +658,8 @@ void orbx_destroy(OrbxHandle* h) {
         if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
     }
     if (h->h_flag) cudaFreeHost(h->h_flag);
+    if (h->ev_s2) cudaEventDestroy(h->ev_s2);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -667,7 +703,11 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         int rc = get_plan(h, width, height, &pe);
         if (rc != ORBX_OK) return rc;
         const int group = std::min(h->prm.max_batch, n_frames);
-        rc = ensure_workspace(h, pe, group);
+        // Consecutive launch groups alternate between two workspace sets and two compute streams, so that the
+        // latency-bound kernels and the tail of every kernel of one group overlap the next group's kernels.
+        // (Profiled runs stay on one stream: their per-stage event times must not overlap.)
+        const bool dual = n_frames > group && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_SINGLE_STREAM);
+        rc = ensure_workspace(h, pe, group, dual ? 2 : 1);
         if (rc != ORBX_OK) return rc;
         rc = set_kernel_attrs(h, pe);
         if (rc != ORBX_OK) return rc;
@@ -684,6 +724,8 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         for (int f0 = 0; f0 < n_frames; f0 += group, ++gi) {
             const int nf = std::min(group, n_frames - f0);
             const int slot = gi & 1;
+            const int set = dual ? slot : 0;
+            cudaStream_t cs = set ? h->stream2 : st;
             const uint8_t* d_imgs;
             long long rs, fs;
             if (host_in) {
@@ -697,28 +739,32 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                                                     row_stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->s_in));
                 }
                 ORBX_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_in));
-                ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[slot], 0));
+                ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_h2d[slot], 0));
                 d_imgs = dst; rs = width; fs = (long long)width * height;
             } else {
                 d_imgs = images + (size_t)f0 * frame_stride; rs = (long long)row_stride; fs = (long long)frame_stride;
             }
             if (host_out) {
                 uint8_t* ob = (uint8_t*)h->d_out + (size_t)slot * out_slot;
-                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[slot], 0));         // slot's previous results copied out
-                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
-                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL);
+                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[slot], 0));         // slot's previous results copied out
+                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
+                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set);
                 if (rc != ORBX_OK) return rc;
-                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], st));
+                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], cs));
                 ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
                 if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
                 if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
                 if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
                 ORBX_CUDA(cudaEventRecord(h->ev_d2h[slot], h->s_out));
             } else {
-                rc = launch_group(h, pe, st, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL);
+                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set);
                 if (rc != ORBX_OK) return rc;
-                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], st));
+                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], cs));
             }
+        }
+        if (dual) {   // join the second compute stream into the caller's stream
+            ORBX_CUDA(cudaEventRecord(h->ev_s2, h->stream2));
+            ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_s2, 0));
         }
         rc = fetch_overflow(h, st);
         if (rc != ORBX_OK) return rc;
@@ -866,6 +912,8 @@ int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height)
     return ORBX_OK;
 }
 
+static const OrbxWs& res_ws(const OrbxHandle* h) { return h->res_set ? h->ws2 : h->ws; }
+
 static int check_frame(OrbxHandle* h, int frame, int level) {
     if (!h) return ORBX_ERR_BAD_ARGUMENT;
     if (!h->cur || frame < 0 || frame >= h->resident_frames) return fail(h, ORBX_ERR_NO_FRAME, "frame not resident");
@@ -880,7 +928,7 @@ int orbx_get_pyramid_level(OrbxHandle* h, int frame, int level, uint8_t* dst, si
     ORBX_CUDA(cudaSetDevice(h->device));
     const OrbxLevel& V = h->cur->plan.lv[level];
     const int b = with_border ? ORBX_EDGE : 0;
-    const uint8_t* src = h->ws.pyr + (size_t)frame * h->ws.pyr_stride + V.plane_off + (size_t)(ORBX_EDGE - b) * V.pitch + (ORBX_PADL - b);
+    const uint8_t* src = res_ws(h).pyr + (size_t)frame * res_ws(h).pyr_stride + V.plane_off + (size_t)(ORBX_EDGE - b) * V.pitch + (ORBX_PADL - b);
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     ORBX_CUDA(cudaMemcpy2D(dst, dst_stride, src, (size_t)V.pitch, (size_t)V.w + 2 * b, (size_t)V.h + 2 * b, cudaMemcpyDeviceToHost));
     return ORBX_OK;
@@ -892,7 +940,7 @@ int orbx_get_blurred_level(OrbxHandle* h, int frame, int level, uint8_t* dst, si
     if (!dst) return fail(h, ORBX_ERR_BAD_ARGUMENT, "null destination");
     ORBX_CUDA(cudaSetDevice(h->device));
     const OrbxLevel& V = h->cur->plan.lv[level];
-    const uint8_t* src = h->ws.blur + (size_t)frame * h->ws.blur_stride + V.blur_off;
+    const uint8_t* src = res_ws(h).blur + (size_t)frame * res_ws(h).blur_stride + V.blur_off;
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     ORBX_CUDA(cudaMemcpy2D(dst, dst_stride, src, (size_t)V.blur_pitch, (size_t)V.w, (size_t)V.h, cudaMemcpyDeviceToHost));
     return ORBX_OK;
@@ -906,12 +954,12 @@ int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* 
     const OrbxLevel& V = P.lv[level];
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     int2 lc;
-    ORBX_CUDA(cudaMemcpy(&lc, h->ws.level_count + (size_t)frame * P.nlevels + level, sizeof(int2), cudaMemcpyDeviceToHost));
+    ORBX_CUDA(cudaMemcpy(&lc, res_ws(h).level_count + (size_t)frame * P.nlevels + level, sizeof(int2), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = lc.x;
     const int n = std::min(lc.x, capacity);
     if (n > 0 && kps) {
         std::vector<OrbxKpRec> rec((size_t)n);
-        ORBX_CUDA(cudaMemcpy(rec.data(), h->ws.kprec + (size_t)frame * h->ws.kp_stride + V.kp_off, (size_t)n * sizeof(OrbxKpRec), cudaMemcpyDeviceToHost));
+        ORBX_CUDA(cudaMemcpy(rec.data(), res_ws(h).kprec + (size_t)frame * res_ws(h).kp_stride + V.kp_off, (size_t)n * sizeof(OrbxKpRec), cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; ++i) {
             kps[i].x = rec[i].x; kps[i].y = rec[i].y; kps[i].size = V.kp_size; kps[i].angle = rec[i].angle;
             kps[i].response = rec[i].response; kps[i].octave = level; kps[i].class_id = -1;
@@ -929,13 +977,13 @@ int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int32_t* xs, 
     const OrbxLevel& V = P.lv[level];
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     int cnt = 0;
-    ORBX_CUDA(cudaMemcpy(&cnt, h->ws.cand_count + (size_t)frame * P.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    ORBX_CUDA(cudaMemcpy(&cnt, res_ws(h).cand_count + (size_t)frame * P.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     cnt = std::min(cnt, V.cand_cap);
     if (n_out) *n_out = cnt;
     const int n = std::min(cnt, capacity);
     if (n > 0) {
         std::vector<uint2> c((size_t)n);
-        ORBX_CUDA(cudaMemcpy(c.data(), h->ws.cand + (size_t)frame * h->ws.cand_stride + V.cand_off, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+        ORBX_CUDA(cudaMemcpy(c.data(), res_ws(h).cand + (size_t)frame * res_ws(h).cand_stride + V.cand_off, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
         const uint32_t CM = (1u << ORBX_COORD_BITS) - 1;
         for (int i = 0; i < n; ++i) {
             if (xs) xs[i] = (int32_t)(c[i].x & CM);

@@ -56,6 +56,7 @@ typedef struct OrbxParams {
 
 #define ORBX_FLAG_PROFILE 1 /* record CUDA-event time per stage (orbx_stage_times) */
 #define ORBX_FLAG_NO_GRAPH 2 /* never replay small launch groups as CUDA graphs */
+#define ORBX_FLAG_SINGLE_STREAM 4 /* do not overlap consecutive launch groups on two compute streams */
 
 /* Same 28-byte layout as cv::KeyPoint. */
 typedef struct OrbxKeyPoint {
