@@ -259,6 +259,19 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 c.level = (uint8_t)l; c.pad = 0;
                 c.ordbase = (uint32_t)(i * V.nCols + j) << ORBX_ORD_CELL_SHIFT;
                 c.xoff = (uint16_t)(j * V.wCell); c.yoff = (uint16_t)(i * V.hCell);
+                {
+                    const int al = (ORBX_PADL + (int)iniX) & 3;
+                    const int nwords = (al + cw + 3) >> 2;
+                    const int wq0 = (al + 3) >> 2;
+                    const int ngrp = ((al + cw - 4) >> 2) - wq0 + 1;
+                    c.nwords = (uint8_t)nwords; c.ngrp = (uint8_t)ngrp; c.wq0 = (uint8_t)wq0;
+                    c.wmagic = (1u << 20) / (unsigned)nwords + 1u;
+                    c.gmagic = (1u << 24) / (unsigned)ngrp + 1u;
+                    const unsigned first_mask = (0xFu << ((al + 3) & 3)) & 0xFu;        // interior starts at byte al+3
+                    const unsigned last_mask = 0xFu >> (3 - ((al + cw - 4) & 3));        // interior ends at byte al+cw-4
+                    c.masks = (uint8_t)(first_mask | (last_mask << 4));
+                    c.reserved = 0;
+                }
                 if ((long long)V.nRows * V.nCols >= (1 << (32 - ORBX_ORD_CELL_SHIFT))) { delete pe; return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "too many cells"); }
                 pe->cells.push_back(c);
                 maxcw = std::max(maxcw, cw); maxch = std::max(maxch, ch);

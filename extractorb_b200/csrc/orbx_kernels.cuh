@@ -237,7 +237,13 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int ci = blockIdx.x * ORBX_FAST_WARPS + wib;
     const int frame = blockIdx.y;
     if (ci >= plan.ncells_total) return;
-    const OrbxCell cell = ws.cells[ci];
+    OrbxCell cell;
+    {
+        const uint4* cp = reinterpret_cast<const uint4*>(ws.cells + ci);
+        const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+        *reinterpret_cast<uint4*>(&cell) = c0;
+        *(reinterpret_cast<uint4*>(&cell) + 1) = c1;
+    }
     const OrbxLevel& L = plan.lv[cell.level];
 
     const int tp = plan.fast_tp;
@@ -246,18 +252,18 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     uint8_t* score = tile + tile_bytes;
     uint16_t* queue = reinterpret_cast<uint16_t*>(score + tile_bytes);
 
-    const int cw = cell.cw, ch = cell.ch;
+    const int ch = cell.ch;
     // ---- stage the cell image (aligned 32-bit cp.async; pixel (r,c) lands at tile[r*tp + a + c]) while the
     // score map is cleared with 128-bit stores ----
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int gx = ORBX_PADL + cell.x0;
     const int a = gx & 3;
-    const int nwords = (a + cw + 3) >> 2;
+    const int nwords = cell.nwords;
     {
         const uint32_t* g32 = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + cell.y0) * L.pitch + (gx - a));
         const int pw = L.pitch >> 2, tpw4 = tp >> 2;
         const int total = nwords * ch;                                   // < 2^13
-        const unsigned wmagic = (1u << 20) / (unsigned)nwords + 1u;      // i / nwords == (i * wmagic) >> 20
+        const unsigned wmagic = cell.wmagic;                             // i / nwords == (i * wmagic) >> 20
         for (int i = lane; i < total; i += 32) {
             const int r = (int)(((unsigned)i * wmagic) >> 20);
             const int wd = i - r * nwords;
@@ -272,13 +278,14 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 
     const int ih = ch - 6;
     // 4-pixel groups (aligned words) covering the interior columns [a+3, a+cw-3)
-    const int wq0 = (a + 3) >> 2;
-    const int ngrp = ((a + cw - 4) >> 2) - wq0 + 1;
+    const int wq0 = cell.wq0;
+    const int ngrp = cell.ngrp;
     const int ngroups = ngrp * ih;
-    const unsigned gmagic = (1u << 24) / (unsigned)ngrp + 1u;  // idx / ngrp == (idx * gmagic) >> 24 (idx < 2^13)
+    const unsigned gmagic = cell.gmagic;                       // idx / ngrp == (idx * gmagic) >> 24 (idx < 2^13)
     const int wq_last = wq0 + ngrp - 1;
-    const unsigned first_mask = (0xFu << ((a + 3) & 3)) & 0xFu;               // interior starts at byte a+3
-    const unsigned last_mask = 0xFu >> (3 - ((a + cw - 4) & 3));              // interior ends at byte a+cw-4
+    // per-word pixel flags live at bits {0, 16, 1, 17} (pixels 0..3): spread the host's 4-bit edge masks likewise
+    auto spread = [](unsigned m) { return (m & 1u) | ((m & 2u) << 15) | ((m & 4u) >> 1) | ((m & 8u) << 14); };
+    const unsigned first_mask = spread(cell.masks & 0xFu), last_mask = spread(cell.masks >> 4), full_mask = 0x00030003u;
     // The reference detects at iniThFAST and re-runs the cell at minThFAST only if that found nothing
     // (:818-838); the same two phases here, the second one skipped when it cannot add anything.
     int qn = 0, n_out = 0, use_th = plan.ini_th;
@@ -296,38 +303,39 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
             const unsigned T1 = (unsigned)(use_th + 1) * 0x00010001u;
             const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
             const int tpw = tp >> 2;
-            for (int base = 0; base < ngroups; base += 32) {
-                const int idx = base + lane;
-                unsigned m4 = 0;
-                int pbase = 0;
-                if (idx < ngroups) {
-                    const int gr = (int)(((unsigned)idx * gmagic) >> 24);
-                    const int wq = wq0 + (idx - gr * ngrp);
-                    const int wi = (gr + 3) * tpw + wq;
-                    const unsigned wc = t32[wi], wl = t32[wi - 1], wr = t32[wi + 1];
-                    const unsigned wu = t32[wi - 3 * tpw], wd = t32[wi + 3 * tpw];
-                    const unsigned lft = __funnelshift_r(wl, wc, 8), rgt = __funnelshift_r(wc, wr, 24);
-                    unsigned z = 0;
+            for (int base = 0; base < ngroups; base += 64) {
+                unsigned mk[2] = {0u, 0u};
+                int pb[2] = {0, 0};
 #pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        const unsigned sel = hlf ? 0x4342u : 0x4140u;
-                        const unsigned c2 = __byte_perm(wc, 0, sel), u2 = __byte_perm(wu, 0, sel), d2 = __byte_perm(wd, 0, sel);
-                        const unsigned l2 = __byte_perm(lft, 0, sel), r2 = __byte_perm(rgt, 0, sel);
-                        const unsigned dk = __vmaxs2(__vmins2(u2, d2), __vmins2(l2, r2));
-                        const unsigned br = __vmins2(__vmaxs2(u2, d2), __vmaxs2(l2, r2));
-                        // lane-wise (c - dk > th) | (br - c > th): bit 15 of (x|0x8000) - (y + th + 1) is set iff x - y > th
-                        const unsigned z1 = (c2 | 0x80008000u) - (dk + T1);
-                        const unsigned z2 = (br | 0x80008000u) - (c2 + T1);
-                        const unsigned zz = (z1 | z2) & 0x80008000u;
-                        z |= ((zz >> 15) & 1u) << (2 * hlf) | ((zz >> 31) & 1u) << (2 * hlf + 1);
+                for (int g = 0; g < 2; ++g) {
+                    const int idx = base + 32 * g + lane;
+                    if (idx < ngroups) {
+                        const int gr = (int)(((unsigned)idx * gmagic) >> 24);
+                        const int wq = wq0 + (idx - gr * ngrp);
+                        const int wi = (gr + 3) * tpw + wq;
+                        const unsigned wc = t32[wi], wl = t32[wi - 1], wr = t32[wi + 1];
+                        const unsigned wu = t32[wi - 3 * tpw], wd = t32[wi + 3 * tpw];
+                        const unsigned lft = __funnelshift_r(wl, wc, 8), rgt = __funnelshift_r(wc, wr, 24);
+                        unsigned z[2];
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            const unsigned sel = hlf ? 0x4342u : 0x4140u;
+                            const unsigned c2 = __byte_perm(wc, 0, sel), u2 = __byte_perm(wu, 0, sel), d2 = __byte_perm(wd, 0, sel);
+                            const unsigned l2 = __byte_perm(lft, 0, sel), r2 = __byte_perm(rgt, 0, sel);
+                            const unsigned dk = __vmaxs2(__vmins2(u2, d2), __vmins2(l2, r2));
+                            const unsigned br = __vmins2(__vmaxs2(u2, d2), __vmaxs2(l2, r2));
+                            // lane-wise (c - dk > th) | (br - c > th): bit 15 of (x|0x8000) - (y + th + 1) is set iff x - y > th
+                            z[hlf] = (((c2 | 0x80008000u) - (dk + T1)) | ((br | 0x80008000u) - (c2 + T1))) & 0x80008000u;
+                        }
+                        // flags of pixels 0,1 at bits 0,16 and of pixels 2,3 at bits 1,17; keep interior pixels only
+                        const unsigned valid = (wq == wq0 ? first_mask : full_mask) & (wq == wq_last ? last_mask : full_mask);
+                        mk[g] = ((z[0] >> 15) | (z[1] >> 14)) & valid;
+                        pb[g] = (gr + 3) * tp + 4 * wq;
                     }
-                    // keep only interior pixels of this word (only a row's first / last word is partial)
-                    m4 = z & (wq == wq0 ? first_mask : 0xFu) & (wq == wq_last ? last_mask : 0xFu);
-                    pbase = (gr + 3) * tp + 4 * wq;
                 }
                 // queue slots by warp prefix sum of the per-lane counts (queue order is irrelevant: every entry
                 // carries its own position)
-                const int cnt = __popc(m4);
+                const int cnt = __popc(mk[0]) + __popc(mk[1]);
                 int inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -336,8 +344,12 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
                 }
                 int pos = qn + inc - cnt;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((m4 >> j) & 1u) queue[pos++] = (uint16_t)(pbase + j);
+                for (int g = 0; g < 2; ++g) {
+                    if (mk[g] & 0x00000001u) queue[pos++] = (uint16_t)(pb[g] + 0);
+                    if (mk[g] & 0x00010000u) queue[pos++] = (uint16_t)(pb[g] + 1);
+                    if (mk[g] & 0x00000002u) queue[pos++] = (uint16_t)(pb[g] + 2);
+                    if (mk[g] & 0x00020000u) queue[pos++] = (uint16_t)(pb[g] + 3);
+                }
                 qn += __shfl_sync(ORBX_FULL_MASK, inc, 31);
             }
         }

@@ -60,13 +60,20 @@ struct OrbxPlan {
 
 // One FAST cell (reference ORBextractor.cc:797-814): the cell image is [x0, x0+cw) x [y0, y0+ch) in
 // level coordinates, FAST evaluates its pixels >= 3 px inside; xoff/yoff = (j*wCell, i*hCell).
-struct OrbxCell {
+struct OrbxCell {          // 32 bytes, read as two uint4
     uint16_t x0, y0;
     uint8_t cw, ch;
     uint8_t level, pad;
     uint32_t ordbase;      // (i * nCols + j) << ORBX_ORD_CELL_SHIFT
     uint16_t xoff, yoff;
+    // precomputed by the host for k_fast_cells (a = (ORBX_PADL + x0) & 3 is the tile's byte alignment)
+    uint32_t wmagic;       // (1<<20)/nwords + 1, nwords = (a + cw + 3) >> 2: staged words per tile row
+    uint32_t gmagic;       // (1<<24)/ngrp + 1,  ngrp = 4-pixel groups per interior row
+    uint8_t nwords, ngrp, wq0, masks;   // wq0 = first group's word; masks = first_mask | last_mask << 4
+    uint32_t reserved;
 };
+
+static_assert(sizeof(OrbxCell) == 32, "OrbxCell is read as two uint4");
 
 // Kept keypoint record written by the quadtree kernel, completed by the describe kernel.
 struct OrbxKpRec {
