@@ -57,6 +57,12 @@ def lib():
         L.orb_oracle_ic_angle.restype = C.c_float
         L.orb_oracle_ic_angle.argtypes = [C.c_void_p, C.c_size_t, _ip]
         L.orb_oracle_descriptor.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
+        L.orb_oracle_stereo.restype = C.c_int
+        L.orb_oracle_stereo.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orb_oracle_descriptor_distance.restype = C.c_int
+        L.orb_oracle_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
         L.ocv_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
         L.ocv_copy_make_border_reflect101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t,
                                                          C.c_int, C.c_int, C.c_int, C.c_int]
@@ -131,6 +137,27 @@ def distribute(xs, ys, scores, min_x, max_x, min_y, max_y, n_quota):
     if n < 0:
         raise ValueError("distribute failed: %d" % n)
     return kept[:n].copy()
+
+
+def stereo_match(kps_l, desc_l, kps_r, desc_r, scale, inv_scale, pyr_l, pyr_r, mb, mbf):
+    """Frame::ComputeStereoMatches restated (oracle/stereo_oracle.c).  pyr_l / pyr_r: lists of 2-D uint8 level images
+    (without border).  -> (mvuRight, mvDepth) float32 arrays."""
+    kps_l = np.ascontiguousarray(kps_l, KP_DTYPE); kps_r = np.ascontiguousarray(kps_r, KP_DTYPE)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8); desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    nl = len(pyr_l)
+    pl = [np.ascontiguousarray(p, np.uint8) for p in pyr_l]
+    pr = [np.ascontiguousarray(p, np.uint8) for p in pyr_r]
+    lw = np.array([p.shape[1] for p in pl], np.int32); lh = np.array([p.shape[0] for p in pl], np.int32)
+    ptr_l = (C.c_void_p * nl)(*[p.ctypes.data for p in pl]); ptr_r = (C.c_void_p * nl)(*[p.ctypes.data for p in pr])
+    pit_l = (C.c_size_t * nl)(*[p.strides[0] for p in pl]); pit_r = (C.c_size_t * nl)(*[p.strides[0] for p in pr])
+    sc = np.ascontiguousarray(scale, np.float32); isc = np.ascontiguousarray(inv_scale, np.float32)
+    u = np.empty(len(kps_l), np.float32); d = np.empty(len(kps_l), np.float32)
+    rc = lib().orb_oracle_stereo(len(kps_l), kps_l.ctypes.data, desc_l.ctypes.data, len(kps_r), kps_r.ctypes.data, desc_r.ctypes.data,
+                                 nl, sc.ctypes.data, isc.ctypes.data, lw.ctypes.data, lh.ctypes.data, ptr_l, pit_l, ptr_r, pit_r,
+                                 float(mb), float(mbf), u.ctypes.data, d.ctypes.data)
+    if rc < 0:
+        raise ValueError("stereo oracle: a right keypoint's row band leaves the image (UB in the reference)")
+    return u, d
 
 
 # ----- the extractor --------------------------------------------------------------------------------

@@ -82,6 +82,38 @@ def run_reference(frames, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, la
         return read_results(fout)
 
 
+REF_STEREO = os.path.join(HERE, "_ref", "ref_stereo")
+
+
+def have_ref_stereo():
+    return os.access(REF_STEREO, os.X_OK)
+
+
+def run_reference_stereo(kps_l, desc_l, kps_r, desc_r, scale, inv_scale, pyr_l, pyr_r, mb, mbf):
+    """Run the unmodified Frame::ComputeStereoMatches (oracle/_ref/ref_stereo).  -> (mvuRight, mvDepth)."""
+    kps_l = np.ascontiguousarray(kps_l, KP_DTYPE); kps_r = np.ascontiguousarray(kps_r, KP_DTYPE)
+    nl = len(pyr_l)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.stin"), os.path.join(td, "out.stou")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<4i", 0x4E495453, nl, len(kps_l), len(kps_r)))
+            f.write(struct.pack("<2f", mb, mbf))
+            f.write(np.ascontiguousarray(scale, "<f4").tobytes()); f.write(np.ascontiguousarray(inv_scale, "<f4").tobytes())
+            f.write(kps_l.tobytes()); f.write(np.ascontiguousarray(desc_l, np.uint8).tobytes())
+            f.write(kps_r.tobytes()); f.write(np.ascontiguousarray(desc_r, np.uint8).tobytes())
+            for a, b in zip(pyr_l, pyr_r):
+                a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+                assert a.shape == b.shape
+                f.write(struct.pack("<2i", a.shape[1], a.shape[0])); f.write(a.tobytes()); f.write(b.tobytes())
+        subprocess.run([REF_STEREO, fin, fout], check=True)
+        buf = open(fout, "rb").read()
+    magic, n = struct.unpack_from("<2i", buf, 0)
+    assert magic == 0x554F5453 and n == len(kps_l)
+    u = np.frombuffer(buf, "<f4", n, 8).copy()
+    d = np.frombuffer(buf, "<f4", n, 8 + 4 * n).copy()
+    return u, d
+
+
 def bench_reference(frames, threads, seconds, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 0)):
     """Time the unmodified reference (normal allocator), one extractor + one frame per thread."""
     with tempfile.TemporaryDirectory() as td:
