@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES"]
+__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
@@ -73,6 +73,7 @@ def load_library():
     L.orbx_get_level_keypoints.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
     L.orbx_get_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, sz]
+    L.orbx_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]
     L.orbx_stage_times.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.orbx_launch_count.restype = C.c_int64
     L.orbx_launch_count.argtypes = [vp]
@@ -263,3 +264,16 @@ class ORBextractor:
     @property
     def stream(self):
         return self._L.orbx_get_stream(self._h)
+
+
+def stereo_match(left, right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
+    """Frame::ComputeStereoMatches (reference src/Frame.cc:813-990) on the GPU: `left` / `right` are the ORBextractor
+    instances that just extracted the two images (their pyramids are still resident), keys/desc what they returned.
+    -> (mvuRight, mvDepth, n_matched); unmatched entries are -1 like in the reference."""
+    keys_l = np.ascontiguousarray(keys_l, KP_DTYPE); keys_r = np.ascontiguousarray(keys_r, KP_DTYPE)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8); desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    u = np.full(len(keys_l), -1.0, np.float32); d = np.full(len(keys_l), -1.0, np.float32)
+    n = C.c_int(0)
+    left._check(left._L.orbx_stereo_match(left._h, right._h, keys_l.ctypes.data, desc_l.ctypes.data, len(keys_l), keys_r.ctypes.data,
+                                          desc_r.ctypes.data, len(keys_r), float(mb), float(mbf), u.ctypes.data, d.ctypes.data, C.byref(n)))
+    return u, d, n.value

@@ -3,7 +3,9 @@
 // C-ABI (include/orbx.h); all pixel work happens in libextractorb_cuda.so.  Reference being replaced:
 // /root/reference/src/orb_extractor/ORBextractor.cc (operator() :1078-1162, constructor :408-475).
 #include "../../include/ORBextractor.h"
+#include "../../include/ORBstereo.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -172,6 +174,29 @@ std::vector<cv::KeyPoint> ORBextractor::DistributeOctTree(const std::vector<cv::
     mLastError.clear();
     out.resize((size_t)n);
     return out;
+}
+
+// Frame::ComputeStereoMatches (reference src/Frame.cc:813-990) through the C-ABI.
+int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<cv::KeyPoint>& mvKeys,
+                         const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,
+                         const cv::Mat& mDescriptorsRight, float mb, float mbf, std::vector<float>& mvuRight,
+                         std::vector<float>& mvDepth) {
+    const int N = (int)mvKeys.size(), Nr = (int)mvKeysRight.size();
+    mvuRight.assign((size_t)N, -1.0f);                                                   // :815-816
+    mvDepth.assign((size_t)N, -1.0f);
+    if (N == 0) return 0;
+    OrbxHandle* hl = left.NativeHandle();
+    OrbxHandle* hr = right.NativeHandle();
+    if (!hl || !hr) return -1;
+    // descriptors as contiguous n x 32 bytes (cv::Mat rows may be strided)
+    std::vector<unsigned char> dl((size_t)N * 32), dr((size_t)std::max(Nr, 1) * 32);
+    for (int i = 0; i < N; ++i) std::memcpy(&dl[(size_t)i * 32], mDescriptors.ptr(i), 32);
+    for (int i = 0; i < Nr; ++i) std::memcpy(&dr[(size_t)i * 32], mDescriptorsRight.ptr(i), 32);
+    int kept = 0;
+    const int rc = orbx_stereo_match(hl, hr, reinterpret_cast<const OrbxKeyPoint*>(mvKeys.data()), dl.data(), N,
+                                     reinterpret_cast<const OrbxKeyPoint*>(mvKeysRight.data()), dr.data(), Nr, mb, mbf,
+                                     mvuRight.data(), mvDepth.data(), &kept);
+    return rc == ORBX_OK ? kept : -1;
 }
 
 // Geometry of one quadtree split (reference :486-542); host-side, for callers that use the node type.

@@ -91,6 +91,7 @@ struct OrbxHandle {
     void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
+    uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // profiling
     std::vector<StageEvents> events;
@@ -578,6 +579,8 @@ int check_overflow(OrbxHandle* h, bool* overflow) {
 
 }  // namespace
 
+static const OrbxWs& res_ws(const OrbxHandle* h) { return h->res_set ? h->ws2 : h->ws; }
+
 extern "C" {
 
 const char* orbx_status_string(int s) {
@@ -663,7 +666,7 @@ void orbx_destroy(OrbxHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_plans(h);
-    cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
+    cudaFree(h->d_stereo); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -917,6 +920,56 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     return rc;
 }
 
+int orbx_stereo_match(OrbxHandle* h, OrbxHandle* right, const OrbxKeyPoint* keys_l, const uint8_t* desc_l, int n_l,
+                      const OrbxKeyPoint* keys_r, const uint8_t* desc_r, int n_r, float mb, float mbf, float* u_right,
+                      float* depth, int* n_matched) {
+    if (!h || !right) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_matched) *n_matched = 0;
+    if (n_l < 0 || n_r < 0 || (n_l > 0 && (!keys_l || !desc_l || !u_right || !depth)) || (n_r > 0 && (!keys_r || !desc_r)) || n_r >= 65535 ||
+        !(mb > 0.f))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad stereo arguments");
+    if (!h->cur || !right->cur || h->resident_frames < 1 || right->resident_frames < 1)
+        return fail(h, ORBX_ERR_NO_FRAME, "both extractors must hold a resident pyramid");
+    if (h->device != right->device || h->cur->plan.width != right->cur->plan.width || h->cur->plan.height != right->cur->plan.height ||
+        h->cur->plan.nlevels != right->cur->plan.nlevels)
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "left and right extractors must share device, image size and level count");
+    if (n_l == 0) return ORBX_OK;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    // scratch layout: kl | dl | kr | dr | u | d | sad | n
+    const size_t o_kl = 0, o_dl = o_kl + align_up((long long)n_l * sizeof(OrbxKeyPoint), 256), o_kr = o_dl + align_up((long long)n_l * 32, 256);
+    const size_t o_dr = o_kr + align_up((long long)std::max(n_r, 1) * sizeof(OrbxKeyPoint), 256), o_u = o_dr + align_up((long long)std::max(n_r, 1) * 32, 256);
+    const size_t o_d = o_u + align_up((long long)n_l * 4, 256), o_s = o_d + align_up((long long)n_l * 4, 256), o_n = o_s + align_up((long long)n_l * 4, 256);
+    int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, o_n + 256, false);
+    if (rc != ORBX_OK) return rc;
+    uint8_t* b = h->d_stereo;
+    cudaStream_t st = h->stream;
+    ORBX_CUDA(cudaStreamSynchronize(right->stream));            // the right pyramid must be complete
+    ORBX_CUDA(cudaMemcpyAsync(b + o_kl, keys_l, (size_t)n_l * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+    ORBX_CUDA(cudaMemcpyAsync(b + o_dl, desc_l, (size_t)n_l * 32, cudaMemcpyHostToDevice, st));
+    if (n_r > 0) {
+        ORBX_CUDA(cudaMemcpyAsync(b + o_kr, keys_r, (size_t)n_r * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+        ORBX_CUDA(cudaMemcpyAsync(b + o_dr, desc_r, (size_t)n_r * 32, cudaMemcpyHostToDevice, st));
+    }
+    OrbxStereoArgs a;
+    a.kl = (const OrbxKeyPoint*)(b + o_kl); a.dl = (const uint32_t*)(b + o_dl); a.nl = n_l;
+    a.kr = (const OrbxKeyPoint*)(b + o_kr); a.dr = (const uint32_t*)(b + o_dr); a.nr = n_r;
+    a.pyr_l = res_ws(h).pyr; a.pyr_r = res_ws(right).pyr;     // frame 0 of each handle's resident group
+    a.mbf = mbf; a.min_d = 0.f; a.max_d = mbf / mb;           // minZ = mb, maxD = mbf / minZ (:844-846)
+    a.th_mul = 1.5f * 1.4f;
+    a.u_right = (float*)(b + o_u); a.depth = (float*)(b + o_d); a.sad = (int*)(b + o_s); a.n_matched = (int*)(b + o_n);
+    k_stereo_match<<<(n_l + 7) / 8, 256, 0, st>>>(h->cur->plan, a);
+    k_stereo_filter<<<1, 256, 0, st>>>(a);
+    h->total_launches += 2; h->stage_launches += 2;
+    ORBX_CUDA(cudaGetLastError());
+    int nm = 0;
+    ORBX_CUDA(cudaMemcpyAsync(u_right, b + o_u, (size_t)n_l * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(depth, b + o_d, (size_t)n_l * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(&nm, b + o_n, 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    if (n_matched) *n_matched = nm;
+    return ORBX_OK;
+}
+
 int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height) {
     if (!h || !h->cur) return ORBX_ERR_NO_FRAME;
     if (level < 0 || level >= h->cur->plan.nlevels) return ORBX_ERR_BAD_ARGUMENT;
@@ -924,8 +977,6 @@ int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height)
     if (height) *height = h->cur->plan.lv[level].h;
     return ORBX_OK;
 }
-
-static const OrbxWs& res_ws(const OrbxHandle* h) { return h->res_set ? h->ws2 : h->ws; }
 
 static int check_frame(OrbxHandle* h, int frame, int level) {
     if (!h) return ORBX_ERR_BAD_ARGUMENT;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/orbx.h"
 #include "orbx_plan.h"
 
 #define ORBX_FULL_MASK 0xffffffffu
@@ -981,6 +982,160 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
             reinterpret_cast<float*>(kps_out)[(fo * cap_per_frame + out_idx) * 7 + lane] = f;
         }
     }
+}
+
+// =================================================================================================
+// S1/S2  Frame::ComputeStereoMatches (reference src/Frame.cc:813-990), the first consumer of the path's outputs.
+// k_stereo_match: one warp per left keypoint -- Hamming search over the right keypoints whose row band covers
+// the left keypoint's row (DescriptorDistance, src/ORBmatcher.cc:2349), then the 11x11 SAD sliding window on the
+// two resident pyramids and the parabola sub-pixel fit.  k_stereo_filter: median-based outlier rejection.
+// =================================================================================================
+struct OrbxStereoArgs {
+    const OrbxKeyPoint* kl; const uint32_t* dl; int nl;
+    const OrbxKeyPoint* kr; const uint32_t* dr; int nr;
+    const uint8_t* pyr_l; const uint8_t* pyr_r;    // frame base of each handle's resident pyramid
+    float mbf, min_d, max_d;                        // minD = 0, maxD = mbf / mb (:844-846)
+    float th_mul;                                   // 1.5f * 1.4f (:979)
+    float* u_right; float* depth; int* sad;         // sad: window distance of an accepted match, else -1
+    int* n_matched;
+};
+
+#define ORBX_TH_HIGH 100   // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36
+#define ORBX_TH_LOW 50     // ORBmatcher::TH_LOW, :37
+
+__global__ void __launch_bounds__(256)
+k_stereo_match(const __grid_constant__ OrbxPlan plan, const OrbxStereoArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (iL >= a.nl) return;
+    const OrbxKeyPoint kpL = a.kl[iL];
+    float out_u = -1.0f, out_d = -1.0f;
+    int out_sad = -1;
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;                                   // vRowIndices[vL], :858
+    const float minU = __fsub_rn(uL, a.max_d), maxU = __fsub_rn(uL, a.min_d);
+    if (maxU >= 0.f && levelL >= 0 && levelL < plan.nlevels) { // :866
+        // ---- best right candidate: smallest (distance, index), distance < TH_HIGH (:869-897) ----
+        const uint4 l0 = *reinterpret_cast<const uint4*>(a.dl + 8 * (size_t)iL), l1 = *reinterpret_cast<const uint4*>(a.dl + 8 * (size_t)iL + 4);
+        unsigned best = ((unsigned)ORBX_TH_HIGH << 16) | 0xffffu;
+        for (int iR = lane; iR < a.nr; iR += 32) {
+            const OrbxKeyPoint kr = a.kr[iR];
+            if (kr.octave < 0 || kr.octave >= plan.nlevels) continue;
+            const float r = __fmul_rn(2.0f, plan.lv[kr.octave].sf);
+            const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));   // :836-837
+            if (row < minr || row > maxr) continue;
+            if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
+            if (!(kr.x >= minU && kr.x <= maxU)) continue;
+            const uint4 r0 = *reinterpret_cast<const uint4*>(a.dr + 8 * (size_t)iR), r1 = *reinterpret_cast<const uint4*>(a.dr + 8 * (size_t)iR + 4);
+            const int dist = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
+                             __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
+            best = min(best, ((unsigned)dist << 16) | (unsigned)iR);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(ORBX_FULL_MASK, best, o));
+        const int bestDist = (int)(best >> 16);
+        if (bestDist < (ORBX_TH_HIGH + ORBX_TH_LOW) / 2) {     // thOrbDist, :818, :900
+            const int bestIdxR = (int)(best & 0xffffu);
+            const OrbxLevel& L = plan.lv[levelL];
+            const float uR0 = a.kr[bestIdxR].x;
+            const float sfi = __fdiv_rn(1.0f, L.sf);           // mvInvScaleFactors[octave], :431-435 of the extractor
+            const float scaleduL = roundf(__fmul_rn(uL, sfi)), scaledvL = roundf(__fmul_rn(vL, sfi));
+            const float scaleduR0 = roundf(__fmul_rn(uR0, sfi));
+            const int w = 5, Lh = 5;
+            const float iniu = scaleduR0 + Lh - w, endu = scaleduR0 + Lh + w + 1;
+            if (!(iniu < 0 || endu >= (float)L.w)) {           // :923-924
+                const uint8_t* imL = a.pyr_l + L.plane_off + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
+                const uint8_t* imR = a.pyr_r + L.plane_off + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
+                const int y0 = (int)(scaledvL - w), x0 = (int)(scaleduL - w), xr0 = (int)(scaleduR0 - w);
+                const int cL = imL[(y0 + w) * L.pitch + x0 + w];
+                int il[4], pr_[4], pc_[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int p = lane + 32 * q;
+                    const int pr = p < 121 ? p / 11 : 0, pc = p < 121 ? p - 11 * (p / 11) : 0;
+                    pr_[q] = pr; pc_[q] = pc;
+                    il[q] = (int)imL[(y0 + pr) * L.pitch + x0 + pc] - cL;      // IL - IL(w,w), :912-913
+                }
+                int bestW = 0x7fffffff, bestinc = 0;
+                float d_prev = 0.f, d_best = 0.f, d_next = 0.f, d_last = 0.f;
+                bool want_next = false;
+#pragma unroll 1
+                for (int inc = -Lh; inc <= Lh; ++inc) {                          // :926-943
+                    const int xr = xr0 + inc;
+                    const int cR = imR[(y0 + w) * L.pitch + xr + w];
+                    int acc = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < 121) acc += abs(il[q] - ((int)imR[(y0 + pr_[q]) * L.pitch + xr + pc_[q]] - cR));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(ORBX_FULL_MASK, acc, o);
+                    const float dist = (float)acc;
+                    if (want_next) { d_next = dist; want_next = false; }
+                    if (acc < bestW) { bestW = acc; bestinc = inc; d_prev = d_last; d_best = dist; want_next = true; }
+                    d_last = dist;
+                }
+                if (bestinc != -Lh && bestinc != Lh) {                           // :945
+                    const float deltaR = __fdiv_rn(__fsub_rn(d_prev, d_next),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d_prev, d_next), __fmul_rn(2.0f, d_best))));   // :953
+                    if (!(deltaR < -1.f || deltaR > 1.f)) {
+                        float bestuR = __fmul_rn(L.sf, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));   // :959
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= a.min_d && disparity < a.max_d) {       // :963
+                            if (disparity <= 0.f) {
+                                disparity = 0.01f;
+                                bestuR = (float)((double)uL - 0.01);
+                            }
+                            out_d = __fdiv_rn(a.mbf, disparity);
+                            out_u = bestuR;
+                            out_sad = bestW;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { a.u_right[iL] = out_u; a.depth[iL] = out_d; a.sad[iL] = out_sad; }
+}
+
+// Outlier rejection (:977-990): median of the accepted window distances (element size/2 of the ascending
+// order), threshold 1.5 * 1.4 * median, matches at or above it are dropped.  One CTA.
+__global__ void __launch_bounds__(256)
+k_stereo_filter(const OrbxStereoArgs a) {
+    __shared__ int s_cnt[8];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    auto block_sum = [&](int v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ORBX_FULL_MASK, v, o);
+        __syncthreads();
+        if ((tid & 31) == 0) s_cnt[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int i = 0; i < 8; ++i) t += s_cnt[i]; s_total = t; }
+        __syncthreads();
+        return s_total;
+    };
+    int mine = 0;
+    for (int i = tid; i < a.nl; i += 256) mine += a.sad[i] >= 0;
+    const int n = block_sum(mine);
+    if (n == 0) { if (tid == 0) *a.n_matched = 0; return; }   // the reference indexes an empty vector here (UB)
+    const int k = n / 2;                                        // vDistIdx[size/2] of the ascending order
+    int lo = 0, hi = 65535;                                     // smallest v with #(sad <= v) >= k + 1
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        int c = 0;
+        for (int i = tid; i < a.nl; i += 256) { const int s = a.sad[i]; c += (s >= 0 && s <= mid); }
+        if (block_sum(c) >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    const float thDist = __fmul_rn(a.th_mul, (float)lo);
+    int kept = 0;
+    for (int i = tid; i < a.nl; i += 256) {
+        const int s = a.sad[i];
+        if (s < 0) continue;
+        if ((float)s < thDist) { ++kept; } else { a.u_right[i] = -1.0f; a.depth[i] = -1.0f; }
+    }
+    kept = block_sum(kept);
+    if (tid == 0) *a.n_matched = kept;
 }
 
 #endif  // ORBX_KERNELS_CUH_

@@ -134,6 +134,17 @@ ORBX_API int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int3
 /* The 7x7 sigma-2 blurred level the descriptors were sampled from (ORBextractor.cc:1126-1127). */
 ORBX_API int orbx_get_blurred_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride);
 
+/* ---- next row of the path --------------------------------------------------
+ * Frame::ComputeStereoMatches (reference src/Frame.cc:813-990): for every left keypoint, Hamming search among the
+ * right keypoints of its row band (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:2349; TH_HIGH 100, TH_LOW 50),
+ * 11x11 SAD refinement on the two pyramids, parabola sub-pixel fit, median-based outlier rejection.
+ * `left` / `right` are the handles that just extracted the two images (their pyramids stay resident on the GPU, so
+ * mvImagePyramid never travels); keys/desc are the host arrays those extractions returned; mb / mbf as in Frame.
+ * u_right / depth (n_l floats each) receive mvuRight / mvDepth (-1 where unmatched); *n_matched the kept matches. */
+ORBX_API int orbx_stereo_match(OrbxHandle* left, OrbxHandle* right, const OrbxKeyPoint* keys_l, const uint8_t* desc_l, int n_l,
+                               const OrbxKeyPoint* keys_r, const uint8_t* desc_r, int n_r, float mb, float mbf,
+                               float* u_right, float* depth, int* n_matched);
+
 /* Sum of CUDA-event milliseconds per stage and number of kernel launches since the last call
  * (requires ORBX_FLAG_PROFILE; resets the accumulators). */
 ORBX_API int orbx_stage_times(OrbxHandle* h, float* ms_per_stage, int64_t* launches);

@@ -44,3 +44,21 @@ def desc_bit_agreement(a, b):
         return 1.0
     x = np.bitwise_xor(a, b)
     return 1.0 - float(np.unpackbits(x).sum()) / (a.size * 8)
+
+
+def make_stereo_pair(left, seed=1):
+    """Synthetic rectified right image: right(x, y) = left(x + d(y), y) with the disparity d growing from 6 px at the
+    top to 40 px at the bottom (a receding ground plane), plus +-3 grey levels of seeded noise."""
+    rng = np.random.default_rng(seed)
+    h, w = left.shape
+    right = np.empty_like(left)
+    for y in range(h):
+        d = 6 + (34 * y) // h
+        right[y, :w - d] = left[y, d:]
+        right[y, w - d:] = left[y, w - 1]
+    noise = rng.integers(-3, 4, left.shape)
+    return np.clip(right.astype(np.int32) + noise, 0, 255).astype(np.uint8)
+
+
+STEREO_MBF = 40.0            # bf (EuRoC-like: baseline 0.11 m x fx 435 px ~ 47.9; any positive value works)
+STEREO_MB = 40.0 / 435.0     # mb = mbf / fx (reference src/Frame.cc:163)

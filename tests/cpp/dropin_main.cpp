@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ORBExtractor.h"   // global-namespace spelling (reference inc/ORBExtractor.h), includes ORBextractor.h
+#include "ORBstereo.h"
 
 static bool load_frames(const char* path, int& n, int& w, int& h, std::vector<uint8_t>& data) {
     FILE* fp = std::fopen(path, "rb");
@@ -39,6 +40,32 @@ int main(int argc, char** argv) {
     if (!out) return 1;
     int32_t hdr[4] = {0x5242524f, n, nlevels, dump};
     std::fwrite(hdr, 4, 4, out);
+
+    if (!std::strcmp(mode, "stereo")) {
+        // frames 0 / 1 = left / right image; the two extractors run on two host threads like the reference's stereo
+        // Frame constructor (src/Frame.cc:109-112), then Frame::ComputeStereoMatches' replacement.  Output:
+        // int32 nL, nL floats mvuRight, nL floats mvDepth, int32 kept.  argv[9] / argv[10] carry bf and fx here.
+        if (n < 2) return 7;
+        const float mbf = (float)std::atof(argv[9]), mb = mbf / (float)std::atof(argv[10]);
+        ORB_SLAM3::ORBextractor exl(nfeatures, scale, nlevels, ini, mn), exr(nfeatures, scale, nlevels, ini, mn);
+        cv::Mat iml(h, w, CV_8UC1, frames.data()), imr(h, w, CV_8UC1, frames.data() + (size_t)w * h);
+        std::vector<cv::KeyPoint> kl, kr; cv::Mat dl, dr; std::vector<int> lapl = {0, 0}, lapr = {0, 0};
+        std::thread tl([&]() { exl(iml, cv::Mat(), kl, dl, lapl); });
+        std::thread tr([&]() { exr(imr, cv::Mat(), kr, dr, lapr); });
+        tl.join(); tr.join();
+        std::vector<float> ur, dp;
+        const int kept = ORB_SLAM3::ComputeStereoMatches(exl, exr, kl, dl, kr, dr, mb, mbf, ur, dp);
+        if (kept < 0) { std::fprintf(stderr, "stereo: %s\n", exl.LastError().c_str()); return 8; }
+        std::fclose(out);
+        out = std::fopen(argv[3], "wb");
+        int32_t nl32 = (int32_t)kl.size(), kept32 = kept;
+        std::fwrite(&nl32, 4, 1, out);
+        std::fwrite(ur.data(), 4, ur.size(), out);
+        std::fwrite(dp.data(), 4, dp.size(), out);
+        std::fwrite(&kept32, 4, 1, out);
+        std::fclose(out);
+        return 0;
+    }
 
     ORBextractor ex(nfeatures, scale, nlevels, ini, mn);          // global alias of ORB_SLAM3::ORBextractor
     if (ex.GetLevels() != nlevels || (int)ex.GetScaleFactors().size() != nlevels || ex.GetScaleFactor() != scale) return 3;

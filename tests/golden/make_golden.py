@@ -62,6 +62,25 @@ def main():
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % case), **out)
         print(case, r["ret"], len(r["kps"]), r["counts"].tolist())
 
+    # Frame::ComputeStereoMatches goldens: the unmodified extractor (ref_extract_bump) on a synthetic rectified
+    # pair, then the unmodified stereo function (oracle/_ref/ref_stereo) on its outputs.
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import make_stereo_pair, synth_frame, STEREO_MB, STEREO_MBF
+    for case, left in (("robot866", imgs["robot866"]), ("synth752", synth_frame(9, 752, 480))):
+        right = make_stereo_pair(left, 1)
+        rl = refio.run_reference(left, nfeatures=1200, lap=(0, 0), dump_pyr=True)[0]
+        rr = refio.run_reference(right, nfeatures=1200, lap=(0, 0), dump_pyr=True)[0]
+        pl = [p[19:-19, 19:-19] for p in rl["pyr"]]
+        pr = [p[19:-19, 19:-19] for p in rr["pyr"]]
+        sc = np.ones(8, np.float32)
+        for i in range(1, 8):
+            sc[i] = np.float32(np.float64(sc[i - 1]) * np.float64(np.float32(1.2)))
+        isc = (np.float32(1.0) / sc).astype(np.float32)
+        u, d = refio.run_reference_stereo(rl["kps"], rl["desc"], rr["kps"], rr["desc"], sc, isc, pl, pr, STEREO_MB, STEREO_MBF)
+        np.savez_compressed(os.path.join(HERE, "stereo_%s.npz" % case), u_right=u, depth=d, n_left=np.int64(len(rl["kps"])),
+                            n_right=np.int64(len(rr["kps"])), mb=np.float32(STEREO_MB), mbf=np.float32(STEREO_MBF))
+        print("stereo", case, len(rl["kps"]), len(rr["kps"]), int((d > 0).sum()))
+
     # primitive KATs from cv2 4.13.0
     rng = np.random.default_rng(4130)
     src = rng.integers(0, 256, (97, 133), dtype=np.uint8)

@@ -80,3 +80,29 @@ def test_cpp_class_multiple_frames_and_empty(demo, images):
                           g["kps"][["x", "y", "size", "response", "octave", "class_id"]])
     assert res[1]["ret"] == 0 and len(res[1]["kps"]) == 0                            # flat frame: descriptors released
     assert len(res[2]["kps"]) > 500
+
+
+@pytest.mark.gpu
+def test_cpp_stereo_matches_reference(demo, images):
+    """include/ORBstereo.h: two extractors on two host threads + ComputeStereoMatches, against the golden of the
+    unmodified reference chain (tests/golden/stereo_robot866.npz)."""
+    import struct
+    from oracle import refio
+    from common import make_stereo_pair, STEREO_MBF
+    left = images["robot866"]
+    frames = np.stack([left, make_stereo_pair(left, 1)])
+    with np.load(os.path.join(ROOT, "tests", "golden", "stereo_robot866.npz")) as z:
+        gu, gd = z["u_right"], z["depth"]
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.orbf"), os.path.join(td, "out.bin")
+        refio.write_frames(fin, frames)
+        # argv: run in out nfeatures scale nlevels ini min <bf> <fx> dump mode
+        r = subprocess.run([demo, "run", fin, fout, "1200", "1.2", "8", "20", "7", repr(STEREO_MBF), "435.0", "0", "stereo"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stderr)
+        buf = open(fout, "rb").read()
+    n = struct.unpack_from("<i", buf, 0)[0]
+    u = np.frombuffer(buf, "<f4", n, 4)
+    d = np.frombuffer(buf, "<f4", n, 4 + 4 * n)
+    kept = struct.unpack_from("<i", buf, 4 + 8 * n)[0]
+    assert n == len(gu) and np.array_equal(u, gu) and np.array_equal(d, gd) and kept == int((gd > 0).sum())
