@@ -85,6 +85,8 @@ struct OrbxHandle {
     int res_set = 0;               // which set holds the resident (last) group
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_s2 = nullptr;
+    cudaStream_t s_side = nullptr;      // side branch of captured graphs: border + blur run beside FAST + quadtree
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* d_pattern_f = nullptr;
     int2* d_angle_w = nullptr;
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;        // input staging (two slots when pipelining host frames)
@@ -450,13 +452,28 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             else k_pyr_resize<false><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
             ++launches;
         }
+        // In a captured graph the border fill and the blur form a side branch: neither FAST nor the quadtree
+        // reads the border or the blurred levels, only k_describe (and pyramid downloads) do.
+        const bool fork = in_capture && stages == STAGES_ALL;
+        cudaStream_t sb = st;
+        if (fork) {
+            ORBX_CUDA(cudaEventRecord(h->ev_fork, st));
+            ORBX_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
+            sb = h->s_side;
+        }
         {
             int max_rows = 0;
             for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
-            k_pyr_border<<<dim3((max_rows + 15) / 16, P.nlevels, nf), dim3(16, 16), 0, st>>>(P, ws);
+            k_pyr_border<<<dim3((max_rows + 15) / 16, P.nlevels, nf), dim3(16, 16), 0, sb>>>(P, ws);
             ++launches;
         }
+        if (fork) {
+            k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, sb>>>(P, ws, 0);
+            ++launches;
+            ORBX_CUDA(cudaEventRecord(h->ev_join, sb));
+        }
     }
+    const bool forked = in_capture && stages == STAGES_ALL;
     if (se) ORBX_CUDA(cudaEventRecord(se->ev[1], st));
     if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
@@ -467,8 +484,12 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
-        k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws);
-        ++launches;
+        if (forked) {
+            ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        } else {
+            k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws, 1);
+            ++launches;
+        }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
         k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
             P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
@@ -622,6 +643,9 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_s2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -675,6 +699,9 @@ void orbx_destroy(OrbxHandle* h) {
     }
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev_s2) cudaEventDestroy(h->ev_s2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->s_side) cudaStreamDestroy(h->s_side);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);

@@ -730,7 +730,7 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // IDP.2A on 16-bit horizontal sums stored as row pairs (rows 2k, 2k+1 share one 32-bit word per column).
 // blockIdx.x indexes a host-built tile table (level | tile_x << 8 | tile_y << 20).
 __global__ void __launch_bounds__(256)
-k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
+k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) {
     constexpr int SROWS = ORBX_BLUR_TH + 6;          // 70 staged rows = 35 row pairs
     constexpr int SPB = ORBX_BLUR_TW + 32;           // staged bytes per row: columns x0-16 .. x0+143 (16-byte chunks)
     constexpr int SW = SPB / 4;
@@ -740,7 +740,9 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int level = tdesc & 0xff;
     const OrbxLevel& L = plan.lv[level];
     const int frame = blockIdx.y;
-    if (ws.level_count[frame * plan.nlevels + level].x == 0) return;  // reference skips empty levels (:1122)
+    // the reference skips levels without keypoints (:1122); when blur runs concurrently with the quadtree (graph
+    // replay of small groups) every level is blurred instead -- the extra output is never read
+    if (skip_empty && ws.level_count[frame * plan.nlevels + level].x == 0) return;
     const int x0 = ((tdesc >> 8) & 0xfff) * ORBX_BLUR_TW, y0 = (tdesc >> 20) * ORBX_BLUR_TH;
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int tid = threadIdx.x;
