@@ -335,3 +335,32 @@ def test_full_size_batch_properties(gpu):
         assert np.all(per_level <= quota + 2)
         assert np.all(d1[f, :n].any(axis=1))
     ext.close()
+
+
+def test_api_contract_errors_and_reuse(gpu, oracle, images):
+    """Error codes of the C-ABI and handle reuse: accessors before any extraction, too small an output capacity,
+    changing image sizes on one handle, continuing after an error."""
+    import ctypes as C
+    ext = gpu.ORBextractor(1000, 1.2, 8, 20, 7)
+    L = ext._L
+    w, h = C.c_int(), C.c_int()
+    assert L.orbx_get_level_size(ext._h, 0, C.byref(w), C.byref(h)) == -8            # ORBX_ERR_NO_FRAME
+    buf = np.zeros((10, 10), np.uint8)
+    assert L.orbx_get_pyramid_level(ext._h, 0, 0, buf.ctypes.data, 10, 0) == -8
+    img = images["robot866"]
+    kps = np.zeros(100, gpu.KP_DTYPE)
+    desc = np.zeros((100, 32), np.uint8)
+    n, mono = C.c_int(), C.c_int()
+    rc = L.orbx_extract(ext._h, img.ctypes.data, 640, 480, 640, 0, 0, kps.ctypes.data, desc.ctypes.data, 100, C.byref(n), C.byref(mono))
+    assert rc == -6 and n.value == 840                                             # ORBX_ERR_CAPACITY, need reported
+    assert L.orbx_extract(ext._h, None, 640, 480, 640, 0, 0, None, None, 0, C.byref(n), C.byref(mono)) == -1   # empty image
+    assert L.orbx_extract(ext._h, img.ctypes.data, 640, 480, 100, 0, 0, None, None, 0, C.byref(n), C.byref(mono)) == -2  # stride < width
+    o = oracle.OracleExtractor(1000, 1.2, 8, 20, 7)
+    for name in ("robot866", "luna", "robot866", "tum_room4"):                     # 640x480 <-> 512x512 on one handle
+        r, k, d = ext(images[name], None, (0, 0))
+        oret, okps, odesc = o.extract(images[name], (0, 0))
+        assert r == oret and kp_bytes_equal(k, okps) and np.array_equal(d, odesc)
+        assert ext.level_size(0) == (images[name].shape[1], images[name].shape[0])
+    assert L.orbx_get_pyramid_level(ext._h, 1, 0, buf.ctypes.data, 10, 0) == -8      # frame 1 is not resident
+    assert L.orbx_get_pyramid_level(ext._h, 0, 99, buf.ctypes.data, 10, 0) == -2     # bad level
+    ext.close()
