@@ -94,7 +94,10 @@ struct OrbxHandle {
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
     uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    // host-buffer pipeline: ORBX_IN_SLOTS input staging slots (the copy engine runs ahead of the two compute
+    // streams), two output staging slots
+    cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr}, ev_in_free[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_d2h[4] = {nullptr, nullptr, nullptr, nullptr};
     // profiling
     std::vector<StageEvents> events;
     size_t events_used = 0;
@@ -648,10 +651,11 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming);
     }
     {
         std::vector<float> pf(1024);
@@ -692,10 +696,11 @@ void orbx_destroy(OrbxHandle* h) {
     drop_plans(h);
     cudaFree(h->d_stereo); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
-    for (int i = 0; i < 2; ++i) {
-        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    for (int i = 0; i < 4; ++i) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_in_free[i]) cudaEventDestroy(h->ev_in_free[i]);
     }
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev_s2) cudaEventDestroy(h->ev_s2);
@@ -761,19 +766,31 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         const size_t o_kps_off = 0, o_desc_off = (size_t)align_up((long long)kp_bytes * group, 256);
         const size_t o_cnt_off = o_desc_off + (size_t)align_up((long long)ds_bytes * group, 256);
         const size_t out_slot = o_cnt_off + (size_t)align_up(8ll * group, 256);
-        if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, 2 * out_slot, false); if (rc != ORBX_OK) return rc; }
-        if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, 2 * in_slot, false); if (rc != ORBX_OK) return rc; }
+        const int n_out_slots = n_frames > group ? 4 : 1;
+        if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, (size_t)n_out_slots * out_slot, false); if (rc != ORBX_OK) return rc; }
+        const int n_in_slots = n_frames > group ? 4 : 1;
+        if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)n_in_slots * in_slot, false); if (rc != ORBX_OK) return rc; }
         int gi = 0;
-        for (int f0 = 0; f0 < n_frames; f0 += group, ++gi) {
-            const int nf = std::min(group, n_frames - f0);
+        for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++gi) {
+            nf = std::min(group, n_frames - f0);
+            if ((host_in || host_out) && group > 32) {
+                // Host buffers: ramp the group size up at the start of the call and down at its end, so that the first
+                // H2D copy (nothing to overlap with yet) and the last kernels + D2H copy (nothing left to overlap) are short.
+                const int up = gi < 4 ? (32 << gi) : group;
+                const int remaining = n_frames - f0;
+                nf = std::min(nf, up);
+                if (remaining <= group) nf = std::min(nf, std::max(32, (remaining + 1) / 2));
+                if (remaining - nf < 16) nf = remaining;                        // do not leave a tiny tail group
+            }
             const int slot = gi & 1;
             const int set = dual ? slot : 0;
             cudaStream_t cs = set ? h->stream2 : st;
             const uint8_t* d_imgs;
             long long rs, fs;
+            const int islot = gi % n_in_slots;
             if (host_in) {
-                uint8_t* dst = h->d_in + (size_t)slot * in_slot;
-                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // slot's previous group consumed
+                uint8_t* dst = h->d_in + (size_t)islot * in_slot;
+                if (gi >= n_in_slots) ORBX_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_in_free[islot], 0));   // slot's previous group consumed
                 if (row_stride == (size_t)width && (nf == 1 || frame_stride == (size_t)width * height)) {
                     ORBX_CUDA(cudaMemcpyAsync(dst, images + (size_t)f0 * frame_stride, (size_t)width * height * nf, cudaMemcpyHostToDevice, h->s_in));
                 } else {
@@ -781,28 +798,30 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                         ORBX_CUDA(cudaMemcpy2DAsync(dst + (size_t)f * width * height, (size_t)width, images + (size_t)(f0 + f) * frame_stride,
                                                     row_stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->s_in));
                 }
-                ORBX_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_in));
-                ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_h2d[slot], 0));
+                ORBX_CUDA(cudaEventRecord(h->ev_h2d[islot], h->s_in));
+                ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_h2d[islot], 0));
                 d_imgs = dst; rs = width; fs = (long long)width * height;
             } else {
                 d_imgs = images + (size_t)f0 * frame_stride; rs = (long long)row_stride; fs = (long long)frame_stride;
             }
             if (host_out) {
-                uint8_t* ob = (uint8_t*)h->d_out + (size_t)slot * out_slot;
-                if (gi >= 2) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[slot], 0));         // slot's previous results copied out
+                const int oslot = gi % n_out_slots;
+                uint8_t* ob = (uint8_t*)h->d_out + (size_t)oslot * out_slot;
+                if (gi >= n_out_slots) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[oslot], 0));   // slot's previous results copied out
                 rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
                                   cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set);
                 if (rc != ORBX_OK) return rc;
-                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], cs));
-                ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+                ORBX_CUDA(cudaEventRecord(h->ev_done[oslot], cs));
+                if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
+                ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[oslot], 0));
                 if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
                 if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
                 if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
-                ORBX_CUDA(cudaEventRecord(h->ev_d2h[slot], h->s_out));
+                ORBX_CUDA(cudaEventRecord(h->ev_d2h[oslot], h->s_out));
             } else {
                 rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set);
                 if (rc != ORBX_OK) return rc;
-                ORBX_CUDA(cudaEventRecord(h->ev_done[slot], cs));
+                if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
             }
         }
         if (dual) {   // join the second compute stream into the caller's stream
