@@ -417,6 +417,9 @@ void drop_plans(OrbxHandle* h) {
 
 enum { STAGES_PYRAMID = 1, STAGES_KEYPOINTS = 2, STAGES_ALL = 3 };
 
+// dynamic shared memory of k_pyr_resize: staged source window + 16-bit horizontal sums + destination-row descriptors
+size_t rs_smem_bytes(int rows, int pitch) { return (size_t)rows * pitch + (size_t)rows * ORBX_RS_TW * 2 + (size_t)ORBX_RS_TH * 16; }
+
 // Launch the stages for `nf` device-resident frames.  Outputs (device pointers, may be NULL) are written
 // at frame index frame_out0 + f.
 int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
@@ -449,10 +452,13 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         for (int l = 1; l < P.nlevels; ++l) {
             const OrbxLevel& V = P.lv[l];
             const dim3 grd((V.w + ORBX_RS_TW - 1) / ORBX_RS_TW, (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nf);
-            const size_t smem = (size_t)pe->rs_rows[l] * pe->rs_pitch[l] + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2;
             const bool area = pe->xtab[V.xtab_off].y == -1;
-            if (area) k_pyr_resize<true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
-            else k_pyr_resize<false><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pe->rs_pitch[l]);
+            const bool fixed = !area && pe->rs_pitch[l] <= ORBX_RS_PITCH;     // specialised instance: constant staging pitch
+            const int pitch = fixed ? ORBX_RS_PITCH : pe->rs_pitch[l];
+            const size_t smem = rs_smem_bytes(pe->rs_rows[l], pitch);
+            if (area) k_pyr_resize<true, 0><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+            else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+            else k_pyr_resize<false, 0><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             ++launches;
         }
         // In a captured graph the border fill and the blur form a side branch: neither FAST nor the quadtree
@@ -579,11 +585,12 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
     }
     size_t rs = 0;
     for (int l = 1; l < pe->plan.nlevels; ++l)
-        rs = std::max(rs, (size_t)pe->rs_rows[l] * pe->rs_pitch[l] + (size_t)pe->rs_rows[l] * ORBX_RS_TW * 2);
+        rs = std::max(rs, rs_smem_bytes(pe->rs_rows[l], std::max(pe->rs_pitch[l], ORBX_RS_PITCH)));
     if (rs > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "scale factor too large for the resize kernel's shared memory");
     if (rs > 48 * 1024) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     return ORBX_OK;
 }

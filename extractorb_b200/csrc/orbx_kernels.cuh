@@ -60,10 +60,38 @@ k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8
 #define ORBX_RS_TW 128
 #define ORBX_RS_TH 64
 
-template <bool AREA>
+// Horizontal pass of one thread: destination column fixed, staged rows g, g+NG, ...  (NG = 0: run-time `ng`).
+// PITCH = 0: run-time staging pitch; otherwise the pitch is a constant and every load has an immediate offset.
+template <bool AREA, int NG, int PITCH>
+__device__ __forceinline__ void rs_hpass(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1, uint16_t* __restrict__ hq,
+                                         int a0, int a1, int g, int ng_rt, int nrows, int pitch_rt) {
+    const int ng = NG ? NG : ng_rt;
+    const int step = ng * (PITCH ? PITCH : pitch_rt);
+    int r = g;
+#pragma unroll 1
+    for (; r + 3 * ng < nrows; r += 4 * ng) {                     // four rows per iteration: loads first, then the math
+        const int u00 = q0[0], u01 = q1[0], u10 = q0[step], u11 = q1[step];
+        const int u20 = q0[2 * step], u21 = q1[2 * step], u30 = q0[3 * step], u31 = q1[3 * step];
+        hq[0] = (uint16_t)(AREA ? (u00 + u01) : ((u00 * a0 + u01 * a1) >> 4));
+        hq[ng * ORBX_RS_TW] = (uint16_t)(AREA ? (u10 + u11) : ((u10 * a0 + u11 * a1) >> 4));
+        hq[2 * ng * ORBX_RS_TW] = (uint16_t)(AREA ? (u20 + u21) : ((u20 * a0 + u21 * a1) >> 4));
+        hq[3 * ng * ORBX_RS_TW] = (uint16_t)(AREA ? (u30 + u31) : ((u30 * a0 + u31 * a1) >> 4));
+        q0 += 4 * step; q1 += 4 * step; hq += 4 * ng * ORBX_RS_TW;
+    }
+    for (; r < nrows; r += ng) {
+        const int u0 = q0[0], u1 = q1[0];
+        hq[0] = (uint16_t)(AREA ? (u0 + u1) : ((u0 * a0 + u1 * a1) >> 4));
+        q0 += step; q1 += step; hq += ng * ORBX_RS_TW;
+    }
+}
+
+#define ORBX_RS_PITCH 192     // staging pitch of the specialised instance (covers scale factors up to ~1.25)
+
+template <bool AREA, int PITCH>
 __global__ void __launch_bounds__(256)
-k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_s) {
+k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
     extern __shared__ __align__(16) uint8_t smem_rs[];
+    const int src_pitch_s = PITCH ? PITCH : src_pitch_rt;
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
     const int tid = threadIdx.x;
@@ -73,71 +101,103 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     const uint8_t* splane = fbase + S.plane_off;
     const int2* xtab = ws.xtab + L.xtab_off;
     const int2* ytab = ws.ytab + L.ytab_off;
-    const int x_last = min(x0 + ORBX_RS_TW, L.w) - 1, y_last = min(y0 + ORBX_RS_TH, L.h) - 1;
+    const int tw = min(ORBX_RS_TW, L.w - x0), th = min(ORBX_RS_TH, L.h - y0);   // this tile's extent
     // source window (inclusive), second taps clamped into the level (their weight is 0 when clamped)
-    const int sx_lo = __ldg(&xtab[x0]).x, sx_hi = min(__ldg(&xtab[x_last]).x + 1, S.w - 1);
-    const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y_last]).x + 1, S.h - 1);
+    const int sx_lo = __ldg(&xtab[x0]).x, sx_hi = min(__ldg(&xtab[x0 + tw - 1]).x + 1, S.w - 1);
+    const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y0 + th - 1]).x + 1, S.h - 1);
     const int nrows = sy_hi - sy_lo + 1;
     const int gcol = ORBX_PADL + sx_lo;            // plane byte column of the first staged pixel
     const int al = gcol & 15;
     const int nvec = (al + (sx_hi - sx_lo + 1) + 15) >> 4;
     uint8_t* s_src = smem_rs;                                           // [src_rows_max][src_pitch_s]
-    uint16_t* s_h = reinterpret_cast<uint16_t*>(smem_rs + (size_t)src_rows_max * src_pitch_s);  // [src_rows_max][TW]
-    // ---- stage (16-byte cp.async; plane rows are 64-byte aligned) ----
+    uint8_t* s_hb = smem_rs + (size_t)src_rows_max * src_pitch_s;       // [src_rows_max][TW] uint16
+    int4* s_yt = reinterpret_cast<int4*>(s_hb + (size_t)src_rows_max * ORBX_RS_TW * 2);   // [TH] row descriptors
+    // ---- stage (16-byte cp.async; plane rows are 64-byte aligned): 16 or 32 lanes per source row ----
     {
         const uint8_t* g = splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al);
-        const int total = nrows * nvec;
-        const unsigned vmagic = (1u << 20) / (unsigned)nvec + 1u;       // i / nvec for i < 2^12
-        for (int i = tid; i < total; i += 256) {
-            const int r = (int)(((unsigned)i * vmagic) >> 20);
-            const int v = i - r * nvec;
-            __pipeline_memcpy_async(s_src + r * src_pitch_s + 16 * v, g + (long long)r * S.pitch + 16 * v, 16);
-        }
+        const int sh = nvec <= 16 ? 4 : 5;
+        const int v0 = tid & ((1 << sh) - 1), rstep = 256 >> sh;
+        for (int v = v0; v < nvec; v += 1 << sh)
+            for (int r = tid >> sh; r < nrows; r += rstep)
+                __pipeline_memcpy_async(s_src + r * src_pitch_s + 16 * v, g + (long long)r * S.pitch + 16 * v, 16);
         __pipeline_commit();
+        // destination-row descriptors: byte offsets of the two source rows inside s_h, vertical coefficients << 16
+        if (tid < th) {
+            const int2 yt = __ldg(&ytab[y0 + tid]);
+            const int r0 = yt.x - sy_lo, r1 = min(yt.x + 1, S.h - 1) - sy_lo;
+            s_yt[tid] = make_int4(r0 * (ORBX_RS_TW * 2), r1 * (ORBX_RS_TW * 2), (int)((unsigned)(yt.y & 0xffff) << 16),
+                                  (int)((unsigned)(yt.y >> 16) << 16));
+        }
         __pipeline_wait_prior(0);
     }
     __syncthreads();
-    // ---- horizontal pass: thread owns one destination column, walks the staged rows ----
+    // ---- horizontal pass: thread owns one destination column, walks the staged rows.  Full tiles: two row
+    // groups of 128 columns; partial tiles: 256 / tw row groups of tw columns, so that no lane idles ----
     {
-        const int c = tid & (ORBX_RS_TW - 1);
-        if (x0 + c <= x_last) {
+        uint16_t* s_h = reinterpret_cast<uint16_t*>(s_hb);
+        if (tw == ORBX_RS_TW) {
+            const int c = tid & (ORBX_RS_TW - 1), g = tid >> 7;
             const int2 xt = __ldg(&xtab[x0 + c]);
-            const uint8_t* p0 = s_src + (xt.x - sx_lo + al);
-            const uint8_t* p1 = s_src + (min(xt.x + 1, S.w - 1) - sx_lo + al);
-            const int a0 = xt.y & 0xffff, a1 = (xt.y >> 16) & 0xffff;
-            uint16_t* hp = s_h + c;
-#pragma unroll 4
-            for (int r = tid >> 7; r < nrows; r += 2) {
-                const int u0 = p0[r * src_pitch_s], u1 = p1[r * src_pitch_s];
-                hp[r * ORBX_RS_TW] = (uint16_t)(AREA ? (u0 + u1) : ((u0 * a0 + u1 * a1) >> 4));
+            const uint8_t* q0 = s_src + (xt.x - sx_lo + al) + g * src_pitch_s;
+            const uint8_t* q1 = q0 + (min(xt.x + 1, S.w - 1) - xt.x);
+            rs_hpass<AREA, 2, PITCH>(q0, q1, s_h + c + g * ORBX_RS_TW, xt.y & 0xffff, (xt.y >> 16) & 0xffff, g, 2, nrows, src_pitch_s);
+        } else {
+            const int ng = 256 / tw;
+            const int g = tid / tw, c = tid - g * tw;
+            if (g < ng) {
+                const int2 xt = __ldg(&xtab[x0 + c]);
+                const uint8_t* q0 = s_src + (xt.x - sx_lo + al) + g * src_pitch_s;
+                const uint8_t* q1 = q0 + (min(xt.x + 1, S.w - 1) - xt.x);
+                rs_hpass<AREA, 0, PITCH>(q0, q1, s_h + c + g * ORBX_RS_TW, xt.y & 0xffff, (xt.y >> 16) & 0xffff, g, ng, nrows, src_pitch_s);
             }
         }
     }
     __syncthreads();
-    // ---- vertical pass: warp w owns rows w, w+8, ...; lane owns 4 columns (one aligned word) ----
-    uint8_t* droi = fbase + L.plane_off + (long long)ORBX_EDGE * L.pitch + ORBX_PADL;
-    const int lane = tid & 31, wrp = tid >> 5;
-    const int x = x0 + 4 * lane;
-    if (x <= x_last) {
-        for (int y = y0 + wrp; y <= y_last; y += 8) {
-            const int2 yt = __ldg(&ytab[y]);
-            const int r0 = yt.x - sy_lo, r1 = min(yt.x + 1, S.h - 1) - sy_lo;
-            const unsigned b0 = (unsigned)(yt.y & 0xffff) << 16, b1 = (unsigned)(yt.y >> 16) << 16;
-            const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + r0 * ORBX_RS_TW + 4 * lane);
-            const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + r1 * ORBX_RS_TW + 4 * lane);
-            const unsigned p0[4] = {h0.x & 0xffffu, h0.x >> 16, h0.y & 0xffffu, h0.y >> 16};
-            const unsigned p1[4] = {h1.x & 0xffffu, h1.x >> 16, h1.y & 0xffffu, h1.y >> 16};
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned v = AREA ? ((p0[j] + p1[j] + 2) >> 2) : ((__umulhi(p0[j], b0) + __umulhi(p1[j], b1) + 2) >> 2);
-                word |= (v & 0xffu) << (8 * j);
-            }
-            uint8_t* d = droi + (long long)y * L.pitch + x;
-            if (x + 3 <= x_last) {
-                *reinterpret_cast<uint32_t*>(d) = word;
+    // ---- vertical pass: one aligned word of 4 destination pixels per item.  t = hi(p0*(b0<<16)) + hi(p1*(b1<<16)) + 2
+    // < 1024, so the four (t >> 2) are packed as two 16-bit pairs, shifted once each and merged with one PRMT.
+    // Full-width tiles: lane = word, warp w owns rows w, w+8, ... (pointers advance by constants).  Partial tiles:
+    // items dealt out linearly so that every lane stays busy; the word that straddles the right edge spills into
+    // the border columns, which k_pyr_border rewrites afterwards. ----
+    {
+        auto vword = [](uint2 h0, uint2 h1, unsigned b0, unsigned b1) -> uint32_t {
+            unsigned t0, t1, t2, t3;
+            if (AREA) {
+                t0 = (h0.x & 0xffffu) + (h1.x & 0xffffu) + 2u; t1 = (h0.x >> 16) + (h1.x >> 16) + 2u;
+                t2 = (h0.y & 0xffffu) + (h1.y & 0xffffu) + 2u; t3 = (h0.y >> 16) + (h1.y >> 16) + 2u;
             } else {
-                for (int j = 0; x + j <= x_last; ++j) d[j] = (uint8_t)(word >> (8 * j));
+                t0 = __umulhi(h0.x & 0xffffu, b0) + __umulhi(h1.x & 0xffffu, b1) + 2u;
+                t1 = __umulhi(h0.x >> 16, b0) + __umulhi(h1.x >> 16, b1) + 2u;
+                t2 = __umulhi(h0.y & 0xffffu, b0) + __umulhi(h1.y & 0xffffu, b1) + 2u;
+                t3 = __umulhi(h0.y >> 16, b0) + __umulhi(h1.y >> 16, b1) + 2u;
+            }
+            const unsigned lo = (t1 * 65536u + t0) >> 2, hi = (t3 * 65536u + t2) >> 2;
+            return __byte_perm(lo, hi, 0x6420);
+        };
+        uint8_t* dtile = fbase + L.plane_off + (long long)(ORBX_EDGE + y0) * L.pitch + ORBX_PADL + x0;
+        const unsigned dpitch = (unsigned)L.pitch;
+        if (tw == ORBX_RS_TW) {
+            const int lane = tid & 31, wrp = tid >> 5;
+            const uint8_t* hb = s_hb + 8 * lane;
+            const int4* ytp = s_yt + wrp;
+            uint8_t* d = dtile + wrp * dpitch + 4 * lane;
+#pragma unroll 2
+            for (int row = wrp; row < th; row += 8) {
+                const int4 yt = *ytp;
+                const uint2 h0 = *reinterpret_cast<const uint2*>(hb + yt.x);
+                const uint2 h1 = *reinterpret_cast<const uint2*>(hb + yt.y);
+                *reinterpret_cast<uint32_t*>(d) = vword(h0, h1, (unsigned)yt.z, (unsigned)yt.w);
+                ytp += 8; d += 8 * dpitch;
+            }
+        } else {
+            const int tw4 = (tw + 3) >> 2, nitems = tw4 * th;
+            const unsigned m = (1u << 20) / (unsigned)tw4 + 1u;           // i / tw4 for i < 2^11
+            for (int i = tid; i < nitems; i += 256) {
+                const unsigned row = ((unsigned)i * m) >> 20;
+                const unsigned cg = (unsigned)i - row * (unsigned)tw4;
+                const int4 yt = s_yt[row];
+                const uint2 h0 = *reinterpret_cast<const uint2*>(s_hb + yt.x + 8 * cg);
+                const uint2 h1 = *reinterpret_cast<const uint2*>(s_hb + yt.y + 8 * cg);
+                *reinterpret_cast<uint32_t*>(dtile + (row * dpitch + 4 * cg)) = vword(h0, h1, (unsigned)yt.z, (unsigned)yt.w);
             }
         }
     }
