@@ -13,7 +13,8 @@ import os
 
 import numpy as np
 
-__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match"]
+__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
+           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
@@ -29,6 +30,15 @@ class OrbxParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("cell_size", C.c_int32),
                 ("max_batch", C.c_int32), ("cand_per_cell", C.c_int32), ("flags", C.c_int32)]
+
+
+class FrameCalib(C.Structure):
+    """OrbxFrameCalib (include/orbx.h): mK, mDistCoef and the image bounds of a Frame."""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 5),
+                ("n_dist", C.c_int32), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
 
 
 class OrbxError(RuntimeError):
@@ -74,6 +84,11 @@ def load_library():
     L.orbx_get_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, sz]
     L.orbx_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]
+    L.orbx_frame_image_bounds.argtypes = [vp, C.POINTER(FrameCalib), i32, i32]
+    L.orbx_frame_undistort_grid.argtypes = [vp, C.POINTER(FrameCalib), vp, i32, vp, vp, vp, C.POINTER(i32)]
+    L.orbx_search_for_initialization.argtypes = [vp, C.POINTER(FrameCalib), vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, C.c_float, i32,
+                                                 vp, C.POINTER(i32)]
+    L.orbx_last_init_fallbacks.argtypes = [vp]
     L.orbx_stage_times.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.orbx_launch_count.restype = C.c_int64
     L.orbx_launch_count.argtypes = [vp]
@@ -277,3 +292,49 @@ def stereo_match(left, right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
     left._check(left._L.orbx_stereo_match(left._h, right._h, keys_l.ctypes.data, desc_l.ctypes.data, len(keys_l), keys_r.ctypes.data,
                                           desc_r.ctypes.data, len(keys_r), float(mb), float(mbf), u.ctypes.data, d.ctypes.data, C.byref(n)))
     return u, d, n.value
+
+
+# ---- the rows after the extractor in a Frame constructor / monocular initialisation ----
+def image_bounds(ext, fx, fy, cx, cy, dist, width, height):
+    """Frame::ComputeImageBounds (reference src/Frame.cc:784-812) -> FrameCalib with mnMinX .. mnMaxY filled in."""
+    c = FrameCalib()
+    c.fx, c.fy, c.cx, c.cy = fx, fy, cx, cy
+    for i, v in enumerate(dist):
+        c.dist[i] = v
+    c.n_dist = len(dist)
+    ext._check(ext._L.orbx_frame_image_bounds(ext._h, C.byref(c), width, height))
+    return c
+
+
+def undistort_grid(ext, calib, keys):
+    """Frame::UndistortKeyPoints + AssignFeaturesToGrid (src/Frame.cc:748-782, :383-417) on the GPU.
+    -> (mvKeysUn, cell_start[64*48+1], cell_items): mGrid[ix][iy] = cell_items[cell_start[ix*48+iy]:cell_start[ix*48+iy+1]]."""
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    n = len(keys)
+    un = np.zeros(n, KP_DTYPE)
+    start = np.zeros(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, np.int32)
+    items = np.zeros(max(n, 1), np.int32)
+    placed = C.c_int(0)
+    ext._check(ext._L.orbx_frame_undistort_grid(ext._h, C.byref(calib), keys.ctypes.data, n, un.ctypes.data, start.ctypes.data,
+                                                items.ctypes.data, C.byref(placed)))
+    return un, start, items[:placed.value].copy()
+
+
+def search_for_initialization(ext, calib, keys_un1, desc1, keys_un2, desc2, cell_start2, cell_items2, prev_matched=None,
+                              window=100, nn_ratio=0.9, check_orientation=True):
+    """ORBmatcher(nn_ratio, check_orientation).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, window)
+    (src/ORBmatcher.cc:705-814).  prev_matched defaults to F1's undistorted keypoint positions, as in
+    Tracking::MonocularInitialization.  -> (nmatches, vnMatches12, vbPrevMatched updated)."""
+    k1 = np.ascontiguousarray(keys_un1, KP_DTYPE); k2 = np.ascontiguousarray(keys_un2, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    cs = np.ascontiguousarray(cell_start2, np.int32); ci = np.ascontiguousarray(cell_items2, np.int32)
+    if prev_matched is None:
+        prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    else:
+        prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = C.c_int(0)
+    ext._check(ext._L.orbx_search_for_initialization(ext._h, C.byref(calib), k1.ctypes.data, d1.ctypes.data, len(k1), k2.ctypes.data,
+                                                     d2.ctypes.data, len(k2), cs.ctypes.data, ci.ctypes.data, prev.ctypes.data, int(window),
+                                                     float(nn_ratio), 1 if check_orientation else 0, m12.ctypes.data, C.byref(n)))
+    return n.value, m12[:len(k1)].copy(), prev

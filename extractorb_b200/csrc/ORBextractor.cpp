@@ -4,6 +4,7 @@
 // /root/reference/src/orb_extractor/ORBextractor.cc (operator() :1078-1162, constructor :408-475).
 #include "../../include/ORBextractor.h"
 #include "../../include/ORBstereo.h"
+#include "../../include/ORBframe.h"
 
 #include <algorithm>
 #include <cmath>
@@ -197,6 +198,67 @@ int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vec
                                      reinterpret_cast<const OrbxKeyPoint*>(mvKeysRight.data()), dr.data(), Nr, mb, mbf,
                                      mvuRight.data(), mvDepth.data(), &kept);
     return rc == ORBX_OK ? kept : -1;
+}
+
+// ---- include/ORBframe.h: Frame post-processing and SearchForInitialization through the C-ABI ----
+bool ComputeImageBounds(ORBextractor& ext, const cv::Mat& K, const cv::Mat& distCoef, int cols, int rows, OrbxFrameCalib& calib) {
+    OrbxHandle* h = ext.NativeHandle();
+    if (!h || K.rows != 3 || K.cols != 3 || K.type() != CV_32FC1 || distCoef.type() != CV_32FC1) return false;
+    const int nd = distCoef.rows * distCoef.cols;
+    if (nd < 4 || nd > 5) return false;
+    std::memset(&calib, 0, sizeof(calib));
+    calib.fx = K.at<float>(0, 0); calib.fy = K.at<float>(1, 1); calib.cx = K.at<float>(0, 2); calib.cy = K.at<float>(1, 2);
+    for (int i = 0; i < nd; ++i) calib.dist[i] = distCoef.rows == 1 ? distCoef.at<float>(0, i) : distCoef.at<float>(i, 0);
+    calib.n_dist = nd;
+    return orbx_frame_image_bounds(h, &calib, cols, rows) == ORBX_OK;
+}
+
+int UndistortAndAssignToGrid(ORBextractor& ext, const OrbxFrameCalib& calib, const std::vector<cv::KeyPoint>& mvKeys,
+                             std::vector<cv::KeyPoint>& mvKeysUn, FrameGridCells& mGrid) {
+    OrbxHandle* h = ext.NativeHandle();
+    if (!h) return -1;
+    const int N = (int)mvKeys.size();
+    mvKeysUn.resize((size_t)N);
+    std::vector<int32_t> start(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0), items((size_t)std::max(N, 1));
+    int placed = 0;
+    const int rc = orbx_frame_undistort_grid(h, &calib, reinterpret_cast<const OrbxKeyPoint*>(mvKeys.data()), N,
+                                             reinterpret_cast<OrbxKeyPoint*>(mvKeysUn.data()), start.data(), items.data(), &placed);
+    if (rc != ORBX_OK) return -1;
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+            const int c = i * FRAME_GRID_ROWS + j;
+            mGrid[i][j].assign(items.begin() + start[c], items.begin() + start[c + 1]);
+        }
+    return placed;
+}
+
+int SearchForInitialization(ORBextractor& ext, const OrbxFrameCalib& calib, const std::vector<cv::KeyPoint>& mvKeysUn1,
+                            const cv::Mat& mDescriptors1, const std::vector<cv::KeyPoint>& mvKeysUn2, const cv::Mat& mDescriptors2,
+                            const FrameGridCells& mGrid2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                            int windowSize, float nnratio, bool checkOrientation) {
+    OrbxHandle* h = ext.NativeHandle();
+    const int n1 = (int)mvKeysUn1.size(), n2 = (int)mvKeysUn2.size();
+    vnMatches12.assign((size_t)n1, -1);                                                         // src/ORBmatcher.cc:708
+    if (!h || (int)vbPrevMatched.size() < n1) return -1;
+    if (n1 == 0) return 0;
+    std::vector<unsigned char> d1((size_t)n1 * 32), d2((size_t)std::max(n2, 1) * 32);
+    for (int i = 0; i < n1; ++i) std::memcpy(&d1[(size_t)i * 32], mDescriptors1.ptr(i), 32);
+    for (int i = 0; i < n2; ++i) std::memcpy(&d2[(size_t)i * 32], mDescriptors2.ptr(i), 32);
+    std::vector<int32_t> start(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0), items;
+    items.reserve((size_t)n2);
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+            for (size_t k = 0; k < mGrid2[i][j].size(); ++k) items.push_back((int32_t)mGrid2[i][j][k]);
+            start[i * FRAME_GRID_ROWS + j + 1] = (int32_t)items.size();
+        }
+    if (items.empty()) items.push_back(0);
+    int nmatches = 0;
+    static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f layout");
+    const int rc = orbx_search_for_initialization(h, &calib, reinterpret_cast<const OrbxKeyPoint*>(mvKeysUn1.data()), d1.data(), n1,
+                                                  reinterpret_cast<const OrbxKeyPoint*>(mvKeysUn2.data()), d2.data(), n2, start.data(),
+                                                  items.data(), reinterpret_cast<float*>(vbPrevMatched.data()), windowSize, nnratio,
+                                                  checkOrientation ? 1 : 0, vnMatches12.data(), &nmatches);
+    return rc == ORBX_OK ? nmatches : -1;
 }
 
 // Geometry of one quadtree split (reference :486-542); host-side, for callers that use the node type.

@@ -18,6 +18,7 @@
 
 #include "../../include/orbx.h"
 #include "orbx_kernels.cuh"
+#include "orbx_frame.cuh"
 
 static const int8_t kPatternHost[1024] = {
 #include "orb_pattern.inc"
@@ -93,7 +94,8 @@ struct OrbxHandle {
     void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
-    uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match
+    uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match / orbx_frame_* / orbx_search_for_initialization
+    int last_init_fallbacks = 0;                             // filtered re-enumerations of the last SearchForInitialization (diagnostic)
     // host-buffer pipeline: ORBX_IN_SLOTS input staging slots (the copy engine runs ahead of the two compute
     // streams), two output staging slots
     cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr}, ev_in_free[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1022,6 +1024,124 @@ int orbx_stereo_match(OrbxHandle* h, OrbxHandle* right, const OrbxKeyPoint* keys
     if (n_matched) *n_matched = nm;
     return ORBX_OK;
 }
+
+// ---- Frame post-processing + SearchForInitialization (orbx_frame.cuh) ----------------------------------------
+static bool calib_ok(const OrbxFrameCalib* c, bool need_bounds) {
+    if (!c || !(c->fx != 0.f) || !(c->fy != 0.f) || c->n_dist < 0 || c->n_dist > 5) return false;
+    if (need_bounds && (!(c->max_x > c->min_x) || !(c->max_y > c->min_y))) return false;
+    return true;
+}
+
+int orbx_frame_image_bounds(OrbxHandle* h, OrbxFrameCalib* calib, int width, int height) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (!calib_ok(calib, false) || width <= 0 || height <= 0) return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad calibration");
+    if (calib->dist[0] == 0.0f) {                                        // src/Frame.cc:805-811
+        calib->min_x = 0.0f; calib->max_x = (float)width; calib->min_y = 0.0f; calib->max_y = (float)height;
+        return ORBX_OK;
+    }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, 256, false);
+    if (rc != ORBX_OK) return rc;
+    float m[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};   // :788-791
+    cudaStream_t st = h->stream;
+    ORBX_CUDA(cudaMemcpyAsync(h->d_stereo, m, sizeof(m), cudaMemcpyHostToDevice, st));
+    k_undistort_points<<<1, 128, 0, st>>>(*calib, (const float2*)h->d_stereo, (float2*)(h->d_stereo + 64), 4);
+    h->total_launches += 1; h->stage_launches += 1;
+    ORBX_CUDA(cudaGetLastError());
+    ORBX_CUDA(cudaMemcpyAsync(m, h->d_stereo + 64, sizeof(m), cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    calib->min_x = std::min(m[0], m[4]); calib->max_x = std::max(m[2], m[6]);                       // :798-802
+    calib->min_y = std::min(m[1], m[3]); calib->max_y = std::max(m[5], m[7]);
+    return ORBX_OK;
+}
+
+int orbx_frame_undistort_grid(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys, int n, OrbxKeyPoint* keys_un,
+                              int32_t* cell_start, int32_t* cell_items, int* n_in_grid) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_in_grid) *n_in_grid = 0;
+    if (!calib_ok(calib, true) || n < 0 || !cell_start || (n > 0 && (!keys || !keys_un || !cell_items)))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad frame-grid arguments");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int nn = std::max(n, 1);
+    const size_t o_k = 0, o_u = o_k + align_up((long long)nn * sizeof(OrbxKeyPoint), 256), o_c = o_u + align_up((long long)nn * sizeof(OrbxKeyPoint), 256);
+    const size_t o_s = o_c + align_up((long long)nn * 4, 256), o_i = o_s + align_up((ORBX_GRID_CELLS + 1) * 4, 256), o_n = o_i + align_up((long long)nn * 4, 256);
+    int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, o_n + 256, false);
+    if (rc != ORBX_OK) return rc;
+    uint8_t* b = h->d_stereo;
+    cudaStream_t st = h->stream;
+    if (n > 0) ORBX_CUDA(cudaMemcpyAsync(b + o_k, keys, (size_t)n * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+    k_frame_undistort_grid<<<1, 1024, 0, st>>>(*calib, (const OrbxKeyPoint*)(b + o_k), n, (OrbxKeyPoint*)(b + o_u), (int*)(b + o_c),
+                                               (int*)(b + o_s), (int*)(b + o_i), (int*)(b + o_n));
+    h->total_launches += 1; h->stage_launches += 1;
+    ORBX_CUDA(cudaGetLastError());
+    int placed = 0;
+    if (n > 0) ORBX_CUDA(cudaMemcpyAsync(keys_un, b + o_u, (size_t)n * sizeof(OrbxKeyPoint), cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(cell_start, b + o_s, (ORBX_GRID_CELLS + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (n > 0) ORBX_CUDA(cudaMemcpyAsync(cell_items, b + o_i, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(&placed, b + o_n, 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    if (n_in_grid) *n_in_grid = placed;
+    return ORBX_OK;
+}
+
+int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1, const uint8_t* desc1, int n1,
+                                   const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2, const int32_t* cell_start2,
+                                   const int32_t* cell_items2, float* prev_matched, int window_size, float nn_ratio,
+                                   int check_orientation, int32_t* matches12, int* n_matches) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_matches) *n_matches = 0;
+    if (!calib_ok(calib, true) || n1 < 0 || n2 < 0 || n2 > 32768 || !cell_start2 ||
+        (n1 > 0 && (!keys_un1 || !desc1 || !prev_matched || !matches12)) || (n2 > 0 && (!keys_un2 || !desc2 || !cell_items2)))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad SearchForInitialization arguments");
+    if (n1 == 0) return ORBX_OK;
+    const int n_items = cell_start2[ORBX_GRID_CELLS];
+    if (n_items < 0 || n_items > n2) return fail(h, ORBX_ERR_BAD_ARGUMENT, "grid does not belong to frame 2");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int m2 = std::max(n2, 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (size_t)align_up((long long)bytes, 256); return at; };
+    const size_t o_k1 = take((size_t)n1 * sizeof(OrbxKeyPoint)), o_d1 = take((size_t)n1 * 32), o_k2 = take((size_t)m2 * sizeof(OrbxKeyPoint));
+    const size_t o_d2 = take((size_t)m2 * 32), o_cs = take((ORBX_GRID_CELLS + 1) * 4), o_ci = take((size_t)m2 * 4), o_pv = take((size_t)n1 * 8);
+    const size_t o_sk = take((size_t)n1 * 32), o_si = take((size_t)n1 * 32), o_sc = take((size_t)n1 * 4), o_m = take((size_t)n1 * 4);
+    const size_t o_p = take((size_t)n1 * 4), o_n = take(8);
+    int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, o, false);
+    if (rc != ORBX_OK) return rc;
+    uint8_t* b = h->d_stereo;
+    cudaStream_t st = h->stream;
+    ORBX_CUDA(cudaMemcpyAsync(b + o_k1, keys_un1, (size_t)n1 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+    ORBX_CUDA(cudaMemcpyAsync(b + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    if (n2 > 0) {
+        ORBX_CUDA(cudaMemcpyAsync(b + o_k2, keys_un2, (size_t)n2 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+        ORBX_CUDA(cudaMemcpyAsync(b + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+        if (n_items > 0) ORBX_CUDA(cudaMemcpyAsync(b + o_ci, cell_items2, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
+    }
+    ORBX_CUDA(cudaMemcpyAsync(b + o_cs, cell_start2, (ORBX_GRID_CELLS + 1) * 4, cudaMemcpyHostToDevice, st));
+    ORBX_CUDA(cudaMemcpyAsync(b + o_pv, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
+    OrbxInitArgs a;
+    a.calib = *calib;
+    a.k1 = (const OrbxKeyPoint*)(b + o_k1); a.d1 = (const uint32_t*)(b + o_d1); a.n1 = n1;
+    a.k2 = (const OrbxKeyPoint*)(b + o_k2); a.d2 = (const uint32_t*)(b + o_d2); a.n2 = n2;
+    a.cell_start2 = (const int*)(b + o_cs); a.cell_items2 = (const int*)(b + o_ci);
+    a.prev = (float*)(b + o_pv); a.r = (float)window_size; a.nn_ratio = nn_ratio; a.check_orientation = check_orientation ? 1 : 0;
+    a.sl_key = (uint4*)(b + o_sk); a.sl_idx = (uint4*)(b + o_si); a.sl_count = (int*)(b + o_sc);
+    a.matches12 = (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.n_matches = (int*)(b + o_n);
+    const size_t smem = (size_t)m2 * 6 + 16;
+    if (smem > 48 * 1024) ORBX_CUDA(cudaFuncSetAttribute(k_init_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_init_shortlist<<<(n1 + 7) / 8, 256, 0, st>>>(a);
+    k_init_resolve<<<1, 256, smem, st>>>(a);
+    h->total_launches += 2; h->stage_launches += 2;
+    ORBX_CUDA(cudaGetLastError());
+    int nm[2] = {0, 0};
+    ORBX_CUDA(cudaMemcpyAsync(matches12, b + o_m, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(prev_matched, b + o_pv, (size_t)n1 * 8, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(nm, b + o_n, 8, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    if (n_matches) *n_matches = nm[0];
+    h->last_init_fallbacks = nm[1];
+    return ORBX_OK;
+}
+
+int orbx_last_init_fallbacks(const OrbxHandle* h) { return h ? h->last_init_fallbacks : 0; }
 
 int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height) {
     if (!h || !h->cur) return ORBX_ERR_NO_FRAME;

@@ -145,6 +145,42 @@ ORBX_API int orbx_stereo_match(OrbxHandle* left, OrbxHandle* right, const OrbxKe
                                const OrbxKeyPoint* keys_r, const uint8_t* desc_r, int n_r, float mb, float mbf,
                                float* u_right, float* depth, int* n_matched);
 
+/* ---- next rows: what every Frame constructor does right after ExtractORB,
+ * and the matcher that consumes it during monocular initialisation -------------------------------------------- */
+#define ORBX_FRAME_GRID_COLS 64 /* FRAME_GRID_COLS, reference inc/Frame.h:40 */
+#define ORBX_FRAME_GRID_ROWS 48 /* FRAME_GRID_ROWS, inc/Frame.h:39 */
+
+typedef struct OrbxFrameCalib {
+    float fx, fy, cx, cy;             /* mK (Pinhole::toK()) */
+    float dist[5];                    /* mDistCoef: k1 k2 p1 p2 [k3]; dist[0] == 0 means "already undistorted" (src/Frame.cc:750) */
+    int32_t n_dist;                   /* 4 or 5 */
+    float min_x, max_x, min_y, max_y; /* mnMinX, mnMaxX, mnMinY, mnMaxY (Frame::ComputeImageBounds) */
+} OrbxFrameCalib;
+
+/* Frame::ComputeImageBounds (src/Frame.cc:784-812): fills min_x .. max_y of *calib for a width x height image
+ * (the four image corners undistorted on the GPU with the arithmetic of cv::undistortPoints). */
+ORBX_API int orbx_frame_image_bounds(OrbxHandle* h, OrbxFrameCalib* calib, int width, int height);
+/* Frame::UndistortKeyPoints (src/Frame.cc:748-782) + Frame::AssignFeaturesToGrid / PosInGrid (:383-417, :726-736),
+ * mono case.  keys -> keys_un (n records); mGrid[ix][iy] = cell_items[cell_start[ix*48+iy] .. cell_start[ix*48+iy+1])
+ * with ascending keypoint index inside a cell; cell_start has 64*48+1 entries, cell_items room for n.
+ * *n_in_grid = keypoints that fell inside the grid. */
+ORBX_API int orbx_frame_undistort_grid(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys, int n,
+                                       OrbxKeyPoint* keys_un, int32_t* cell_start, int32_t* cell_items, int* n_in_grid);
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:705-814) with GetFeaturesInArea (src/Frame.cc:655-724),
+ * DescriptorDistance (:2349-2365) and ComputeThreeMaxima (:2303-2344).  keys_un*, desc*: mvKeysUn / mDescriptors of
+ * the two frames; cell_start2 / cell_items2: frame 2's grid from orbx_frame_undistort_grid; prev_matched: n1 (x, y)
+ * pairs, vbPrevMatched, updated in place; matches12: n1 ints (vnMatches12, -1 = none); *n_matches = return value.
+ * nn_ratio / check_orientation are the ORBmatcher constructor arguments (:40).  n2 <= 32768. */
+ORBX_API int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1,
+                                            const uint8_t* desc1, int n1, const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2,
+                                            const int32_t* cell_start2, const int32_t* cell_items2, float* prev_matched,
+                                            int window_size, float nn_ratio, int check_orientation, int32_t* matches12,
+                                            int* n_matches);
+
+/* Diagnostic: how many keypoints of the last orbx_search_for_initialization call had to be re-enumerated because their
+ * 8-entry shortlist was exhausted by already-matched candidates (the slow, still exact, path). */
+ORBX_API int orbx_last_init_fallbacks(const OrbxHandle* h);
+
 /* Sum of CUDA-event milliseconds per stage and number of kernel launches since the last call
  * (requires ORBX_FLAG_PROFILE; resets the accumulators). */
 ORBX_API int orbx_stage_times(OrbxHandle* h, float* ms_per_stage, int64_t* launches);

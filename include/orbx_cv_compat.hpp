@@ -162,6 +162,18 @@ public:
     Size size() const { return Size(cols, rows); }
     bool isContinuous() const { return step == (size_t)cols * elemSize() || rows <= 1; }
 
+    // cv::Mat::reshape(cn): same data, `cn` channels per element (rows unchanged; the matrix must be continuous).
+    Mat reshape(int cn) const {
+        Mat m(*this);
+        const int total_per_row = cols * CV_MAT_CN(type_);
+        m.type_ = CV_MAKETYPE(CV_MAT_DEPTH(type_), cn);
+        m.cols = total_per_row / cn;
+        return m;
+    }
+
+    // Single-index access for row / column vectors (cv::Mat::at<T>(int i0)).
+    template <typename T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (size_t)i * step); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (size_t)i * step); }
     template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
     template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }

@@ -300,3 +300,35 @@ float ocv_fast_atan2(float y, float x) {
     if (y < 0) a = 360.f - a;
     return a;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * undistortPoints (OpenCV calib3d cvUndistortPointsInternal, default TermCriteria(MAX_ITER, 5, 0.01) so only the
+ * iteration count applies; no rotation, no tilt, P = K).  Call sites: src/Frame.cc:767, :797.
+ * Pinned against cv2 4.13.0 (tests/test_oracle_frame.py, tests/golden/frame_kat.npz).
+ * ---------------------------------------------------------------------------------------------- */
+void ocv_undistort_points_f32(const float* xy_in, int n, float fxf, float fyf, float cxf, float cyf, const float* dist,
+                              int n_dist, float* xy_out) {
+    double k[14] = {0};
+    for (int i = 0; i < n_dist && i < 14; ++i) k[i] = (double)dist[i];
+    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; ++i) {
+        double x = ((double)xy_in[2 * i] - cx) * ifx, y = ((double)xy_in[2 * i + 1] - cy) * ify;
+        const double x0 = x, y0 = y;
+        if (n_dist > 0) {
+            for (int j = 0; j < 5; ++j) {
+                const double r2 = x * x + y * y;
+                const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+                if (icdist < 0) { x = x0; y = y0; break; }
+                const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+                const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+                x = (x0 - deltaX) * icdist;
+                y = (y0 - deltaY) * icdist;
+            }
+        }
+        /* RR = P * I: [fx 0 cx; 0 fy cy; 0 0 1] */
+        const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        xy_out[2 * i] = (float)(xx * ww);
+        xy_out[2 * i + 1] = (float)(yy * ww);
+    }
+}

@@ -55,6 +55,13 @@ void ocv_gaussian_blur_7x7_s2_u8(const uint8_t* src, int w, int h, size_t sstep,
 /* cv::fastAtan2(y, x) scalar path, degrees in [0, 360]. */
 float ocv_fast_atan2(float y, float x);
 
+/* cv::undistortPoints(src, dst, K, distCoeffs, noArray(), P) for CV_32FC2 points with K = P =
+ * [fx 0 cx; 0 fy cy; 0 0 1] given as floats and n_dist in {4, 5} coefficients (k1 k2 p1 p2 [k3]): the default
+ * 5 fixed-point iterations in double precision (no FMA), result rounded to float.  Call sites:
+ * Frame::UndistortKeyPoints src/Frame.cc:767, Frame::ComputeImageBounds :797.  xy_in may alias xy_out. */
+void ocv_undistort_points_f32(const float* xy_in, int n, float fx, float fy, float cx, float cy, const float* dist,
+                              int n_dist, float* xy_out);
+
 #ifdef __cplusplus
 }
 #endif

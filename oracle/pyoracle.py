@@ -63,6 +63,17 @@ def lib():
                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orb_oracle_descriptor_distance.restype = C.c_int
         L.orb_oracle_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.orb_oracle_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orb_oracle_undistort_keypoints.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orb_oracle_assign_grid.restype = C.c_int
+        L.orb_oracle_assign_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orb_oracle_features_in_area.restype = C.c_int
+        L.orb_oracle_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_search_for_initialization.restype = C.c_int
+        L.orb_oracle_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.ocv_undistort_points_f32.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         L.ocv_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
         L.ocv_copy_make_border_reflect101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t,
                                                          C.c_int, C.c_int, C.c_int, C.c_int]
@@ -158,6 +169,72 @@ def stereo_match(kps_l, desc_l, kps_r, desc_r, scale, inv_scale, pyr_l, pyr_r, m
     if rc < 0:
         raise ValueError("stereo oracle: a right keypoint's row band leaves the image (UB in the reference)")
     return u, d
+
+
+# ----- Frame post-processing + SearchForInitialization (oracle/frame_oracle.c) -----------------------
+GRID_COLS, GRID_ROWS = 64, 48
+CALIB_DTYPE = np.dtype([("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4"), ("dist", "<f4", (5,)), ("n_dist", "<i4"),
+                        ("min_x", "<f4"), ("max_x", "<f4"), ("min_y", "<f4"), ("max_y", "<f4")])
+
+
+def make_calib(fx, fy, cx, cy, dist, width, height):
+    """OrbOracleCalib with the image bounds of Frame::ComputeImageBounds filled in."""
+    c = np.zeros(1, CALIB_DTYPE)
+    c["fx"], c["fy"], c["cx"], c["cy"] = fx, fy, cx, cy
+    c["dist"][0, :len(dist)] = dist
+    c["n_dist"] = len(dist)
+    lib().orb_oracle_image_bounds(c.ctypes.data, width, height)
+    return c
+
+
+def undistort_points(xy, fx, fy, cx, cy, dist):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    d = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(xy)
+    lib().ocv_undistort_points_f32(xy.ctypes.data, len(xy), fx, fy, cx, cy, d.ctypes.data, len(d), out.ctypes.data)
+    return out
+
+
+def undistort_keypoints(calib, kps):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty_like(kps)
+    lib().orb_oracle_undistort_keypoints(calib.ctypes.data, kps.ctypes.data, len(kps), out.ctypes.data)
+    return out
+
+
+def assign_grid(calib, kps_un):
+    """-> (cell_start[64*48+1], cell_items): mGrid[ix][iy] = cell_items[cell_start[ix*48+iy] : cell_start[ix*48+iy+1]]."""
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    start = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+    items = np.zeros(max(len(kps_un), 1), np.int32)
+    n = lib().orb_oracle_assign_grid(calib.ctypes.data, kps_un.ctypes.data, len(kps_un), start.ctypes.data, items.ctypes.data)
+    return start, items[:n].copy()
+
+
+def features_in_area(calib, kps_un, start, items, x, y, r, min_level=-1, max_level=-1):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    items = np.ascontiguousarray(items, np.int32)
+    out = np.zeros(max(len(kps_un), 1), np.int32)
+    n = lib().orb_oracle_features_in_area(calib.ctypes.data, kps_un.ctypes.data, start.ctypes.data, items.ctypes.data, x, y, r,
+                                          min_level, max_level, out.ctypes.data, len(out))
+    return out[:n].copy()
+
+
+def search_for_initialization(calib, kps_un1, desc1, kps_un2, desc2, start2, items2, prev_matched=None, window=100, nn_ratio=0.9,
+                              check_orientation=True):
+    """ORBmatcher::SearchForInitialization restated.  -> (nmatches, vnMatches12, vbPrevMatched updated)."""
+    k1 = np.ascontiguousarray(kps_un1, KP_DTYPE); k2 = np.ascontiguousarray(kps_un2, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    items2 = np.ascontiguousarray(items2, np.int32)
+    if prev_matched is None:
+        prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    else:
+        prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = lib().orb_oracle_search_for_initialization(calib.ctypes.data, k1.ctypes.data, d1.ctypes.data, len(k1), k2.ctypes.data, d2.ctypes.data,
+                                                   len(k2), start2.ctypes.data, items2.ctypes.data, prev.ctypes.data, window, nn_ratio,
+                                                   1 if check_orientation else 0, m12.ctypes.data)
+    return n, m12[:len(k1)].copy(), prev
 
 
 # ----- the extractor --------------------------------------------------------------------------------

@@ -114,6 +114,55 @@ def run_reference_stereo(kps_l, desc_l, kps_r, desc_r, scale, inv_scale, pyr_l, 
     return u, d
 
 
+REF_FRAME = os.path.join(HERE, "_ref", "ref_frame")
+
+
+def have_ref_frame():
+    return os.access(REF_FRAME, os.X_OK)
+
+
+def run_reference_frame(width, height, fx, fy, cx, cy, dist, kps1, desc1, kps2, desc2, window=100, nn_ratio=0.9,
+                        check_orientation=True, prev_matched=None):
+    """Run the unmodified Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid and
+    ORBmatcher::SearchForInitialization (oracle/_ref/ref_frame).  -> dict."""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    n1, n2 = len(kps1), len(kps2)
+    d = np.zeros(5, "<f4"); d[:len(dist)] = dist
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.frin"), os.path.join(td, "out.frou")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<9i", 0x4E495246, width, height, n1, n2, window, 1 if check_orientation else 0, len(dist),
+                                0 if prev_matched is None else 1))
+            f.write(struct.pack("<5f", nn_ratio, fx, fy, cx, cy)); f.write(d.tobytes())
+            f.write(kps1.tobytes()); f.write(np.ascontiguousarray(desc1, np.uint8).tobytes())
+            f.write(kps2.tobytes()); f.write(np.ascontiguousarray(desc2, np.uint8).tobytes())
+            if prev_matched is not None:
+                f.write(np.ascontiguousarray(prev_matched, "<f4").tobytes())
+        subprocess.run([REF_FRAME, fin, fout], check=True)
+        buf = open(fout, "rb").read()
+    return parse_frame_output(buf, n1, n2)
+
+
+def parse_frame_output(buf, n1=None, n2=None):
+    """Result file of oracle/ref_frame_main.cpp (and of tests/cpp/dropin_main.cpp in `frame` mode)."""
+    magic, a, b = struct.unpack_from("<3i", buf, 0)
+    n1 = a if n1 is None else n1
+    n2 = b if n2 is None else n2
+    assert magic == 0x554F5246 and a == n1 and b == n2
+    off = 12
+    out = {"bounds": np.frombuffer(buf, "<f4", 4, off).copy()}; off += 16
+    out["keys_un1"] = np.frombuffer(buf, KP_DTYPE, n1, off).copy(); off += 28 * n1
+    out["keys_un2"] = np.frombuffer(buf, KP_DTYPE, n2, off).copy(); off += 28 * n2
+    for k in (1, 2):
+        start = np.frombuffer(buf, "<i4", 64 * 48 + 1, off).copy(); off += 4 * (64 * 48 + 1)
+        items = np.frombuffer(buf, "<i4", int(start[-1]), off).copy(); off += 4 * int(start[-1])
+        out["cell_start%d" % k], out["cell_items%d" % k] = start, items
+    out["nmatches"] = struct.unpack_from("<i", buf, off)[0]; off += 4
+    out["matches12"] = np.frombuffer(buf, "<i4", n1, off).copy(); off += 4 * n1
+    out["prev_matched"] = np.frombuffer(buf, "<f4", 2 * n1, off).copy().reshape(-1, 2)
+    return out
+
+
 def bench_reference(frames, threads, seconds, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lap=(0, 0)):
     """Time the unmodified reference (normal allocator), one extractor + one frame per thread."""
     with tempfile.TemporaryDirectory() as td:

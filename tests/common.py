@@ -62,3 +62,67 @@ def make_stereo_pair(left, seed=1):
 
 STEREO_MBF = 40.0            # bf (EuRoC-like: baseline 0.11 m x fx 435 px ~ 47.9; any positive value works)
 STEREO_MB = 40.0 / 435.0     # mb = mbf / fx (reference src/Frame.cc:163)
+
+
+def second_view(img, angle_deg=0.0, dx=0, dy=0, seed=5, noise=4):
+    """A second camera view of `img` for the monocular-initialisation tests: rotation about the image centre by
+    `angle_deg` and an integer shift, sampled with nearest-neighbour look-ups (integer arithmetic after one float64
+    coordinate transform), plus +-`noise` grey levels of seeded noise."""
+    h, w = img.shape
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    a = np.deg2rad(angle_deg)
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    xs = np.cos(a) * (xx - cx) + np.sin(a) * (yy - cy) + cx - dx
+    ys = -np.sin(a) * (xx - cx) + np.cos(a) * (yy - cy) + cy - dy
+    xi = np.clip(np.floor(xs + 0.5).astype(np.int64), 0, w - 1)
+    yi = np.clip(np.floor(ys + 0.5).astype(np.int64), 0, h - 1)
+    out = img[yi, xi].astype(np.int32)
+    rng = np.random.default_rng(seed)
+    out += rng.integers(-noise, noise + 1, img.shape)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# Camera models of the datasets BASELINE.json names (ORB-SLAM3 example settings): (fx, fy, cx, cy), distortion
+FRAME_CAMERAS = {
+    "tum640": (640, 480, (517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+    "euroc752": (752, 480, (458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+    "nodist640": (640, 480, (500.0, 500.0, 320.0, 240.0), (0.0, 0.0, 0.0, 0.0)),
+}
+# (case, camera, seed, nfeatures, rotation of the second view, dx, dy)
+FRAME_CASES = [
+    ("tum640", "tum640", 3, 2000, 4.0, 7, -4),
+    ("euroc752", "euroc752", 11, 5000, -12.0, -15, 9),
+    ("nodist640", "nodist640", 21, 1000, 0.0, 3, 2),
+]
+
+
+def random_frame_pair(seed, n1=1500, n2=1600, w=640, h=480):
+    """Two synthetic keypoint/descriptor sets with many ambiguous matches (descriptors are noisy copies of a few
+    prototypes, positions cluster): exercises re-matching (vnMatches21 take-overs), ties and the rotation filter of
+    ORBmatcher::SearchForInitialization without any image."""
+    rng = np.random.default_rng(seed)
+    kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+    proto = rng.integers(0, 256, (60, 32), dtype=np.uint8)
+    centres = rng.random((25, 2)) * [w - 80, h - 80] + 40
+
+    def make(n):
+        k = np.zeros(n, kp_dtype)
+        c = centres[rng.integers(0, len(centres), n)]
+        k["x"] = np.clip(np.round(c[:, 0] + rng.normal(0, 25, n)), 19, w - 20)
+        k["y"] = np.clip(np.round(c[:, 1] + rng.normal(0, 25, n)), 19, h - 20)
+        k["size"] = 31
+        k["angle"] = (rng.random(n) * 360).astype(np.float32)
+        k["angle"][rng.random(n) < 0.5] = 90.0
+        k["response"] = rng.integers(7, 200, n)
+        k["octave"] = (rng.random(n) < 0.25) * rng.integers(1, 8, n)
+        k["class_id"] = -1
+        d = proto[rng.integers(0, len(proto), n)].copy()
+        flips = rng.integers(0, 256, (n, 12))
+        for j in range(12):
+            on = rng.random(n) < 0.6
+            d[np.arange(n)[on], flips[on, j] // 8] ^= (1 << (flips[on, j] % 8)).astype(np.uint8)
+        return k, d
+
+    k1, d1 = make(n1)
+    k2, d2 = make(n2)
+    return k1, d1, k2, d2

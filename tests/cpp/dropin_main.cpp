@@ -11,6 +11,7 @@
 
 #include "ORBExtractor.h"   // global-namespace spelling (reference inc/ORBExtractor.h), includes ORBextractor.h
 #include "ORBstereo.h"
+#include "ORBframe.h"
 
 static bool load_frames(const char* path, int& n, int& w, int& h, std::vector<uint8_t>& data) {
     FILE* fp = std::fopen(path, "rb");
@@ -63,6 +64,64 @@ int main(int argc, char** argv) {
         std::fwrite(ur.data(), 4, ur.size(), out);
         std::fwrite(dp.data(), 4, dp.size(), out);
         std::fwrite(&kept32, 4, 1, out);
+        std::fclose(out);
+        return 0;
+    }
+
+    if (!std::strcmp(mode, "frame")) {
+        // frames 0 / 1 = two views.  What the monocular Frame constructor does after ExtractORB (src/Frame.cc:307-347) and
+        // Tracking::MonocularInitialization's matcher call (src/Tracking.cc: ORBmatcher matcher(0.9,true);
+        // matcher.SearchForInitialization(mInitialFrame, mCurrentFrame, mvbPrevMatched, mvIniMatches, 100)), through
+        // include/ORBframe.h.  argv[13..]: fx fy cx cy n_dist d0..d4 window check_orientation.  The output has the layout of
+        // oracle/ref_frame_main.cpp so that one parser reads both programs.
+        if (n < 2 || argc < 25) return 7;
+        cv::Mat K = cv::Mat::zeros(3, 3, CV_32FC1);
+        K.at<float>(0, 0) = (float)std::atof(argv[13]); K.at<float>(1, 1) = (float)std::atof(argv[14]);
+        K.at<float>(0, 2) = (float)std::atof(argv[15]); K.at<float>(1, 2) = (float)std::atof(argv[16]); K.at<float>(2, 2) = 1.f;
+        const int nd = std::atoi(argv[17]);
+        cv::Mat dist(nd, 1, CV_32FC1);
+        for (int i = 0; i < nd; ++i) dist.at<float>(i, 0) = (float)std::atof(argv[18 + i]);
+        const int window = std::atoi(argv[23]), check = std::atoi(argv[24]);
+        ORB_SLAM3::ORBextractor ex(nfeatures, scale, nlevels, ini, mn);
+        std::vector<cv::KeyPoint> keys[2], un[2];
+        cv::Mat desc[2];
+        static ORB_SLAM3::FrameGridCells grid[2];
+        OrbxFrameCalib calib;
+        std::vector<int> lap = {lap0, lap1};
+        for (int k = 0; k < 2; ++k) {
+            cv::Mat im(h, w, CV_8UC1, frames.data() + (size_t)k * w * h);
+            if (ex(im, cv::Mat(), keys[k], desc[k], lap) < 0) { std::fprintf(stderr, "frame: %s\n", ex.LastError().c_str()); return 8; }
+            desc[k] = desc[k].clone();
+            if (k == 0 && !ORB_SLAM3::ComputeImageBounds(ex, K, dist, w, h, calib)) return 9;
+            if (ORB_SLAM3::UndistortAndAssignToGrid(ex, calib, keys[k], un[k], grid[k]) < 0) return 10;
+        }
+        std::vector<cv::Point2f> prev(un[0].size());
+        for (size_t i = 0; i < un[0].size(); ++i) prev[i] = un[0][i].pt;
+        std::vector<int> m12;
+        const int nm = ORB_SLAM3::SearchForInitialization(ex, calib, un[0], desc[0], un[1], desc[1], grid[1], prev, m12, window, 0.9f, check != 0);
+        if (nm < 0) { std::fprintf(stderr, "frame: %s\n", ex.LastError().c_str()); return 11; }
+        std::fclose(out);
+        out = std::fopen(argv[3], "wb");
+        int32_t oh[3] = {0x554f5246, (int32_t)un[0].size(), (int32_t)un[1].size()};
+        std::fwrite(oh, 4, 3, out);
+        float b[4] = {calib.min_x, calib.max_x, calib.min_y, calib.max_y};
+        std::fwrite(b, 4, 4, out);
+        for (int k = 0; k < 2; ++k) std::fwrite(un[k].data(), sizeof(cv::KeyPoint), un[k].size(), out);
+        for (int k = 0; k < 2; ++k) {
+            std::vector<int32_t> start(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0), items;
+            for (int ix = 0; ix < FRAME_GRID_COLS; ++ix)
+                for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) {
+                    for (size_t j = 0; j < grid[k][ix][iy].size(); ++j) items.push_back((int32_t)grid[k][ix][iy][j]);
+                    start[ix * FRAME_GRID_ROWS + iy + 1] = (int32_t)items.size();
+                }
+            std::fwrite(start.data(), 4, start.size(), out);
+            std::fwrite(items.data(), 4, items.size(), out);
+        }
+        int32_t nm32 = nm;
+        std::fwrite(&nm32, 4, 1, out);
+        std::vector<int32_t> m(m12.begin(), m12.end());
+        std::fwrite(m.data(), 4, m.size(), out);
+        std::fwrite(prev.data(), 8, prev.size(), out);
         std::fclose(out);
         return 0;
     }

@@ -106,3 +106,35 @@ def test_cpp_stereo_matches_reference(demo, images):
     d = np.frombuffer(buf, "<f4", n, 4 + 4 * n)
     kept = struct.unpack_from("<i", buf, 4 + 8 * n)[0]
     assert n == len(gu) and np.array_equal(u, gu) and np.array_equal(d, gd) and kept == int((gd > 0).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["tum640", "nodist640"])
+def test_cpp_frame_matches_reference(demo, case):
+    """include/ORBframe.h: extraction of two views, ComputeImageBounds, UndistortAndAssignToGrid (mvKeysUn + mGrid) and
+    SearchForInitialization, against the golden of the unmodified reference chain (tests/golden/frame_*.npz)."""
+    from oracle import refio
+    from common import FRAME_CAMERAS, FRAME_CASES, second_view, synth_frame
+    _, cam, seed, nf, ang, dx, dy = next(c for c in FRAME_CASES if c[0] == case)
+    w, h, K, dist = FRAME_CAMERAS[cam]
+    im1 = synth_frame(seed, w, h)
+    frames = np.stack([im1, second_view(im1, ang, dx, dy, seed + 100)])
+    with np.load(os.path.join(ROOT, "tests", "golden", "frame_%s.npz" % case)) as z:
+        g = {k: z[k] for k in z.files}
+    d = list(dist) + [0.0] * (5 - len(dist))
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.orbf"), os.path.join(td, "out.bin")
+        refio.write_frames(fin, frames)
+        cmd = [demo, "run", fin, fout, str(nf), "1.2", "8", "20", "7", "0", "1000", "0", "frame"] + [repr(float(v)) for v in K] + \
+              [str(len(dist))] + [repr(float(v)) for v in d] + ["100", "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stderr)
+        out = refio.parse_frame_output(open(fout, "rb").read())
+    assert len(out["keys_un1"]) == int(g["n1"]) and len(out["keys_un2"]) == int(g["n2"])
+    assert out["bounds"].tobytes() == g["bounds"].tobytes()
+    for k in ("1", "2"):
+        xy = np.stack([out["keys_un" + k]["x"], out["keys_un" + k]["y"]], 1)
+        assert xy.tobytes() == g["un_xy" + k].tobytes()
+        assert np.array_equal(out["cell_start" + k], g["cell_start" + k]) and np.array_equal(out["cell_items" + k], g["cell_items" + k])
+    assert out["nmatches"] == int(g["nmatches_w100_o1"]) and np.array_equal(out["matches12"], g["matches12_w100_o1"])
+    assert out["prev_matched"].tobytes() == g["prev_w100_o1"].tobytes()
