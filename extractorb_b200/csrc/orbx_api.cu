@@ -1103,7 +1103,7 @@ int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, c
     const size_t o_k1 = take((size_t)n1 * sizeof(OrbxKeyPoint)), o_d1 = take((size_t)n1 * 32), o_k2 = take((size_t)m2 * sizeof(OrbxKeyPoint));
     const size_t o_d2 = take((size_t)m2 * 32), o_cs = take((ORBX_GRID_CELLS + 1) * 4), o_ci = take((size_t)m2 * 4), o_pv = take((size_t)n1 * 8);
     const size_t o_sk = take((size_t)n1 * 32), o_si = take((size_t)n1 * 32), o_sc = take((size_t)n1 * 4), o_m = take((size_t)n1 * 4);
-    const size_t o_p = take((size_t)n1 * 4), o_n = take(8);
+    const size_t o_p = take((size_t)n1 * 4), o_al = take((size_t)n1 * 4), o_n = take(8);
     int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, o, false);
     if (rc != ORBX_OK) return rc;
     uint8_t* b = h->d_stereo;
@@ -1124,7 +1124,7 @@ int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, c
     a.cell_start2 = (const int*)(b + o_cs); a.cell_items2 = (const int*)(b + o_ci);
     a.prev = (float*)(b + o_pv); a.r = (float)window_size; a.nn_ratio = nn_ratio; a.check_orientation = check_orientation ? 1 : 0;
     a.sl_key = (uint4*)(b + o_sk); a.sl_idx = (uint4*)(b + o_si); a.sl_count = (int*)(b + o_sc);
-    a.matches12 = (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.n_matches = (int*)(b + o_n);
+    a.matches12 = (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.act_list = (int*)(b + o_al); a.n_matches = (int*)(b + o_n);
     const size_t smem = (size_t)m2 * 6 + 16;
     if (smem > 48 * 1024) ORBX_CUDA(cudaFuncSetAttribute(k_init_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_init_shortlist<<<(n1 + 7) / 8, 256, 0, st>>>(a);

@@ -177,6 +177,7 @@ struct OrbxInitArgs {
     uint4* sl_key; uint4* sl_idx; int* sl_count;
     int* matches12;         // n1
     int* pushed;            // n1: bestIdx2 at the time i1 was matched (never reset), -1 otherwise
+    int* act_list;          // n1: scratch, the keypoints k_init_resolve has to visit, ascending
     int* n_matches;
 };
 
@@ -274,7 +275,7 @@ k_init_shortlist(const OrbxInitArgs a) {
     const int lane = threadIdx.x & 31;
     const int i1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i1 >= a.n1) return;
-    if (lane == 0) { a.matches12[i1] = -1; a.pushed[i1] = -1; }
+    if (lane == 0) { a.matches12[i1] = -1; a.pushed[i1] = -1; if (i1 == 0) a.n_matches[1] = 0; }
     unsigned key[ORBX_SHORT_K];
     int idx[ORBX_SHORT_K];
     int count = 0;
@@ -297,11 +298,15 @@ k_init_shortlist(const OrbxInitArgs a) {
     }
 }
 
-// One CTA.  Warp 0 walks frame 1's keypoints in index order (the reference's loop carries vMatchedDistance and
-// vnMatches21 from one keypoint to the next); all lanes execute the same instructions on the same values.  A
-// keypoint whose best unfiltered candidate is already above TH_LOW can never match (filtering only removes
-// candidates), so only the others are visited.  The rotation histogram, the three-maxima filter, the
-// vbPrevMatched update and the final count run on all threads afterwards.
+// One CTA of 256 threads = 32 keypoint slots x 8 shortlist entries.  The reference's loop carries vMatchedDistance and
+// vnMatches21 from one keypoint to the next; here the 32 keypoints of a chunk are evaluated together against the
+// current state, and the longest prefix for which that provably equals the one-at-a-time result is applied: a keypoint
+// "clashes" when an earlier pending keypoint of the chunk matches a candidate that is still live in its own shortlist
+// (that match would lower vMatchedDistance under it), or when its shortlist ran dry (it then has to be re-enumerated
+// against the exact state).  Everything before the first clash is applied in parallel, then the rest is evaluated again;
+// the first pending keypoint can never clash, so every round makes progress.  A keypoint whose best unfiltered candidate
+// is already above TH_LOW can never match (filtering only removes candidates) and is not visited at all.  The rotation
+// histogram, the three-maxima filter, the vbPrevMatched update and the final count run on all threads afterwards.
 __global__ void __launch_bounds__(256)
 k_init_resolve(const OrbxInitArgs a) {
     extern __shared__ __align__(16) uint8_t smem_init[];
@@ -310,77 +315,137 @@ k_init_resolve(const OrbxInitArgs a) {
     __shared__ int s_hist[ORBX_MATCH_HISTO];
     __shared__ int s_ind[3];
     __shared__ int s_nm;
+    __shared__ __align__(16) int s_mb[32];   // speculative bestIdx2 of each slot (-1: no match)
+    __shared__ unsigned s_pending;    // slots not resolved yet
+    __shared__ int s_stop;            // first slot that clashes in this round (32: none)
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < a.n2; i += blockDim.x) { m21[i] = -1; vmd[i] = 0xffffu; }
     if (tid < ORBX_MATCH_HISTO) s_hist[tid] = 0;
-    if (tid == 0) s_nm = 0;
-    __syncthreads();
+    if (tid == 0) { s_nm = 0; s_pending = 0u; }
     int n_fallback = 0;
-    if (tid < 32) {
-        // The shortlists of 32 consecutive keypoints are staged in shared memory (the next chunk's loads are in flight
-        // while the current one is walked).  For one keypoint, lane q < 8 tests shortlist entry q against the current
-        // vMatchedDistance; two ballots give the first and second live entry.
-        __shared__ unsigned s_key[32][ORBX_SHORT_K];
-        __shared__ int s_idx[32][ORBX_SHORT_K];
-        __shared__ int s_cnt[32];
-        const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), zero = make_uint4(0, 0, 0, 0);
-        uint4 mk = none, mk2 = none, mi = zero, mi2 = zero;
-        int mc = 0;
-        if (lane < a.n1) { mk = a.sl_key[2 * lane]; mk2 = a.sl_key[2 * lane + 1]; mi = a.sl_idx[2 * lane]; mi2 = a.sl_idx[2 * lane + 1]; mc = a.sl_count[lane]; }
-        const int q = lane & (ORBX_SHORT_K - 1);
-        for (int base = 0; base < a.n1; base += 32) {
-            *reinterpret_cast<uint4*>(&s_key[lane][0]) = mk; *reinterpret_cast<uint4*>(&s_key[lane][4]) = mk2;
-            *reinterpret_cast<uint4*>(&s_idx[lane][0]) = mi; *reinterpret_cast<uint4*>(&s_idx[lane][4]) = mi2;
-            s_cnt[lane] = mc;
-            unsigned act = __ballot_sync(0xffffffffu, mc > 0 && (int)(mk.x >> 22) <= ORBX_MATCH_TH_LOW);
-            const int nxt = base + 32 + lane;
-            mk = none; mk2 = none; mi = zero; mi2 = zero; mc = 0;
-            if (nxt < a.n1) { mk = a.sl_key[2 * nxt]; mk2 = a.sl_key[2 * nxt + 1]; mi = a.sl_idx[2 * nxt]; mi2 = a.sl_idx[2 * nxt + 1]; mc = a.sl_count[nxt]; }
-            __syncwarp();
-            while (act) {
-                const int src = __ffs(act) - 1;
-                act &= act - 1;
-                const int i1 = base + src;
-                const unsigned key = s_key[src][q];
-                const int idx = s_idx[src][q];
-                const bool valid = key != 0xffffffffu;
-                const bool live = valid && (int)vmd[valid ? idx : 0] > (int)(key >> 22);              // :744
-                const unsigned lm = __ballot_sync(0xffffffffu, live) & ((1u << ORBX_SHORT_K) - 1u);
-                const unsigned vm = __ballot_sync(0xffffffffu, valid) & ((1u << ORBX_SHORT_K) - 1u);
-                const int b = __ffs(lm) - 1, s2 = __ffs(lm & (lm - 1u)) - 1;
-                int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
-                if (s_cnt[src] > __popc(vm) && s2 < 0) {
-                    // the shortlist ran dry before two live candidates were found: enumerate again with the filter
-                    uint32_t dq[8];
-                    const uint4* qd = reinterpret_cast<const uint4*>(a.d1 + (size_t)i1 * 8);
-                    const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
-                    dq[0] = q0.x; dq[1] = q0.y; dq[2] = q0.z; dq[3] = q0.w; dq[4] = q1.x; dq[5] = q1.y; dq[6] = q1.z; dq[7] = q1.w;
-                    unsigned fkey[ORBX_SHORT_K];
-                    int fidx[ORBX_SHORT_K];
-                    int cnt2;
-                    init_enumerate<true>(a, a.prev[2 * i1], a.prev[2 * i1 + 1], dq, vmd, fkey, fidx, cnt2);
+    const int slot = tid >> 3, q = tid & 7, gl = lane & 24;
+    const unsigned* sl_key = reinterpret_cast<const unsigned*>(a.sl_key);
+    const int* sl_idx = reinterpret_cast<const int*>(a.sl_idx);
+    // ---- ordered list of the keypoints that can match at all: shortlist not empty and its best distance <= TH_LOW ----
+    __shared__ int s_scan[8];
+    __shared__ int s_nact;
+    {
+        const int per = (a.n1 + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int lo = min(tid * per, a.n1), hi = min(lo + per, a.n1);
+        int c = 0;
+        for (int i = lo; i < hi; ++i) c += (a.sl_count[i] > 0 && (int)(sl_key[(size_t)i * ORBX_SHORT_K] >> 22) <= ORBX_MATCH_TH_LOW) ? 1 : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_scan[tid >> 5] = inc;
+        __syncthreads();
+        int off = inc - c;
+        for (int w = 0; w < (tid >> 5); ++w) off += s_scan[w];
+        if (tid == (int)blockDim.x - 1) s_nact = off + c;
+        for (int i = lo; i < hi; ++i)
+            if (a.sl_count[i] > 0 && (int)(sl_key[(size_t)i * ORBX_SHORT_K] >> 22) <= ORBX_MATCH_TH_LOW) a.act_list[off++] = i;
+        __syncthreads();
+    }
+    const int nact = s_nact;
+    unsigned nkey = 0xffffffffu;
+    int nidx = 0, ncnt = 0, ni1 = -1;
+    if (slot < nact) {
+        ni1 = a.act_list[slot];
+        nkey = sl_key[(size_t)ni1 * ORBX_SHORT_K + q]; nidx = sl_idx[(size_t)ni1 * ORBX_SHORT_K + q]; ncnt = a.sl_count[ni1];
+    }
+    for (int base = 0; base < nact; base += 32) {
+        const int i1 = ni1;
+        const unsigned key = nkey;
+        const int idx = nidx, cnt = ncnt;
+        {   // the next chunk's shortlist entries are in flight while this chunk is resolved
+            const int nx = base + 32 + slot;
+            nkey = 0xffffffffu; nidx = 0; ncnt = 0; ni1 = -1;
+            if (nx < nact) {
+                ni1 = a.act_list[nx];
+                nkey = sl_key[(size_t)ni1 * ORBX_SHORT_K + q]; nidx = sl_idx[(size_t)ni1 * ORBX_SHORT_K + q]; ncnt = a.sl_count[ni1];
+            }
+        }
+        const bool valid = key != 0xffffffffu;
+        const int dist = (int)(key >> 22);
+        const int listed = __popc((__ballot_sync(0xffffffffu, valid) >> gl) & 0xffu);
+        __syncthreads();                                                  // previous chunk fully applied; s_pending == 0
+        if (q == 0 && i1 >= 0) atomicOr(&s_pending, 1u << slot);
+        __syncthreads();
+        while (true) {
+            const unsigned pending = s_pending;
+            if (pending == 0u) break;
+            const bool mine = (pending >> slot) & 1u;
+            const bool first = mine && (pending & ((1u << slot) - 1u)) == 0u;
+            // ---- evaluate every pending slot against the current state ----
+            const bool live = mine && valid && (int)vmd[valid ? idx : 0] > dist;                        // :744
+            const unsigned lm = (__ballot_sync(0xffffffffu, live) >> gl) & 0xffu;
+            const int b = __ffs(lm) - 1, s2 = __ffs(lm & (lm - 1u)) - 1;
+            const bool dry = mine && cnt > listed && s2 < 0;
+            int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+            {
+                const unsigned bk = __shfl_sync(0xffffffffu, key, gl | (b & 7));
+                const int bi = __shfl_sync(0xffffffffu, idx, gl | (b & 7));
+                const unsigned sk = __shfl_sync(0xffffffffu, key, gl | (s2 & 7));
+                if (b >= 0) { bestDist = (int)(bk >> 22); bestIdx2 = bi; }
+                if (s2 >= 0) bestDist2 = (int)(sk >> 22);
+            }
+            // the first pending slot sees the exact state: if its shortlist ran dry, its warp enumerates again with the filter
+            if (__any_sync(0xffffffffu, first && dry)) {
+                const int fl = __ffs(__ballot_sync(0xffffffffu, first && dry)) - 1;           // a lane of that slot
+                const int fi1 = __shfl_sync(0xffffffffu, i1, fl);
+                uint32_t dq[8];
+                const uint4* qd = reinterpret_cast<const uint4*>(a.d1 + (size_t)fi1 * 8);
+                const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+                dq[0] = q0.x; dq[1] = q0.y; dq[2] = q0.z; dq[3] = q0.w; dq[4] = q1.x; dq[5] = q1.y; dq[6] = q1.z; dq[7] = q1.w;
+                unsigned fkey[ORBX_SHORT_K];
+                int fidx[ORBX_SHORT_K];
+                int cnt2;
+                init_enumerate<true>(a, a.prev[2 * fi1], a.prev[2 * fi1 + 1], dq, vmd, fkey, fidx, cnt2);
+                if (first) {
+                    bestDist = 0x7fffffff; bestDist2 = 0x7fffffff; bestIdx2 = -1;
                     if (fkey[0] != 0xffffffffu) { bestDist = (int)(fkey[0] >> 22); bestIdx2 = fidx[0]; }
                     if (fkey[1] != 0xffffffffu) bestDist2 = (int)(fkey[1] >> 22);
-                    ++n_fallback;
-                } else {
-                    if (b >= 0) { bestDist = (int)(s_key[src][b] >> 22); bestIdx2 = s_idx[src][b]; }
-                    if (s2 >= 0) bestDist2 = (int)(s_key[src][s2] >> 22);
                 }
-                if (bestDist <= ORBX_MATCH_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio)) {   // :758-760
-                    if (lane == 0) {
-                        const int old = m21[bestIdx2];
-                        if (old >= 0) a.matches12[old] = -1;                                // :762-766
-                        a.matches12[i1] = bestIdx2;
-                        a.pushed[i1] = bestIdx2;
-                        m21[bestIdx2] = i1;
-                        vmd[bestIdx2] = (uint16_t)bestDist;
-                    }
-                    __syncwarp();
+                if (lane == fl) ++n_fallback;
+            }
+            const bool match = mine && bestIdx2 >= 0 && bestDist <= ORBX_MATCH_TH_LOW &&
+                               (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio);                 // :758-760
+            if (q == 0) s_mb[slot] = match ? bestIdx2 : -1;
+            if (tid == 0) s_stop = 32;
+            __syncthreads();
+            // ---- clash detection ----
+            bool clash = dry && !first;
+            if (live && !first) {
+                // does an earlier slot's speculative match land on this live candidate?  (32 slots = 8 x int4)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int4 m = reinterpret_cast<const int4*>(s_mb)[v];
+                    clash = clash || (4 * v + 0 < slot && m.x == idx) || (4 * v + 1 < slot && m.y == idx) ||
+                            (4 * v + 2 < slot && m.z == idx) || (4 * v + 3 < slot && m.w == idx);
                 }
             }
-            __syncwarp();
+            if (clash) atomicMin(&s_stop, slot);
+            __syncthreads();
+            // ---- apply the clash-free prefix ----
+            const int stop = s_stop;
+            if (mine && slot < stop && q == 0) {
+                if (match) {
+                    const int old = m21[bestIdx2];
+                    if (old >= 0) a.matches12[old] = -1;                                    // :762-766
+                    a.matches12[i1] = bestIdx2;
+                    a.pushed[i1] = bestIdx2;
+                    m21[bestIdx2] = i1;
+                    vmd[bestIdx2] = (uint16_t)bestDist;
+                }
+                atomicAnd(&s_pending, ~(1u << slot));
+            }
+            __syncthreads();
         }
     }
+    if (n_fallback) atomicAdd(&a.n_matches[1], n_fallback);
     __threadfence_block();
     __syncthreads();
     // ---- rotation histogram over every keypoint that was ever matched (:772-783; entries of matches that were
@@ -431,5 +496,5 @@ k_init_resolve(const OrbxInitArgs a) {
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_nm, local);
     __syncthreads();
-    if (tid == 0) { a.n_matches[0] = s_nm; a.n_matches[1] = n_fallback; }   // [1]: filtered re-enumerations (diagnostic)
+    if (tid == 0) a.n_matches[0] = s_nm;   // n_matches[1]: filtered re-enumerations (diagnostic), cleared by k_init_shortlist
 }

@@ -35,9 +35,9 @@ def sass_line_map(kernel):
         if l.startswith(".text.") or l.startswith("//--------------------- .text"):
             if m:
                 break
-        g = re.search(r'//## File ".*?", line (\d+)', l)
+        g = re.search(r'//## File "(.*?)", line (\d+)', l)
         if g:
-            cur = int(g.group(1))
+            cur = (os.path.basename(g.group(1)), int(g.group(2)))
             continue
         g = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if g:
@@ -75,13 +75,21 @@ def main():
         v[4] += int(r[col["L1 Wavefronts Shared"]] or 0)
     tot = sum(v[0] for v in agg.values()) or 1
     smp = sum(v[2] for v in agg.values()) or 1
-    src = open(SRC).read().split("\n")
+    srcs = {}
+    for f in os.listdir(os.path.dirname(SRC)):
+        try:
+            srcs[f] = open(os.path.join(os.path.dirname(SRC), f)).read().split("\n")
+        except (OSError, UnicodeDecodeError):
+            pass
     print("total warp instructions %d, stall samples %d" % (tot, smp))
     print(" inst%  stall%  thr/inst  L1tagReq(M)  smemWave(M)  line  source")
     for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
-        text = src[ln - 1].strip()[:86] if ln and ln <= len(src) else ""
-        print("%5.1f  %5.1f   %5.1f   %9.2f   %9.2f   %4s  %s" % (100.0 * v[0] / tot, 100.0 * v[2] / smp, v[1] / max(v[0], 1),
-                                                              v[3] / 1e6, v[4] / 1e6, ln, text))
+        fname, lno = ln if ln else ("", 0)
+        src = srcs.get(fname, [])
+        text = src[lno - 1].strip()[:86] if lno and lno <= len(src) else ""
+        tag = ("%s:%d" % (fname.replace("orbx_", "").replace(".cuh", ""), lno)) if lno else "?"
+        print("%5.1f  %5.1f   %5.1f   %9.2f   %9.2f   %-12s %s" % (100.0 * v[0] / tot, 100.0 * v[2] / smp, v[1] / max(v[0], 1),
+                                                                 v[3] / 1e6, v[4] / 1e6, tag, text))
 
 
 if __name__ == "__main__":
