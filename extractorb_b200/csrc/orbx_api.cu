@@ -115,6 +115,13 @@ int fail(OrbxHandle* h, int code, const std::string& msg) {
     return code;
 }
 
+// number of leading pyramid levels whose quadtrees run with ORBX_QT_THREADS_BIG threads
+inline int qt_big_levels(const OrbxPlan& P) {
+    int nbig = 0;
+    while (nbig < P.nlevels && (long long)P.lv[nbig].w * P.lv[nbig].h >= ORBX_QT_BIG_PIXELS) ++nbig;
+    return nbig;
+}
+
 #define ORBX_CUDA(call)                                                                              \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -491,9 +498,17 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
-        if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws);
-        else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws);
-        ++launches;
+        // levels of a megapixel or more hold tens of thousands of candidates each: their quadtrees get 1024-thread CTAs
+        const int nbig = qt_big_levels(P);
+        if (nbig > 0) {
+            k_octree<ORBX_QT_THREADS_BIG><<<dim3(nbig, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, 0);
+            ++launches;
+        }
+        if (nbig < P.nlevels) {
+            if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws, nbig);
+            else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws, nbig);
+            ++launches;
+        }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
         if (forked) {
             ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -531,7 +546,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     for (auto& g : pe->graphs)
         if (g.exec && g.key == key) {
             ORBX_CUDA(cudaGraphLaunch(g.exec, st));
-            const int64_t n = (stages & STAGES_PYRAMID ? pe->plan.nlevels + 1 : 0) + (stages & STAGES_KEYPOINTS ? 4 : 0);
+            const int64_t n = (stages & STAGES_PYRAMID ? pe->plan.nlevels + 1 : 0) + (stages & STAGES_KEYPOINTS ? 4 + (qt_big_levels(pe->plan) > 0 && qt_big_levels(pe->plan) < pe->plan.nlevels ? 1 : 0) : 0);
             h->stage_launches += n; h->total_launches += n;
             h->cur = pe; h->resident_frames = nf; h->res_set = 0;
             return ORBX_OK;
@@ -584,6 +599,7 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
     if (pe->qt_smem > 48 * 1024) {
         ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
         ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
+        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
     }
     size_t rs = 0;
     for (int l = 1; l < pe->plan.nlevels; ++l)
@@ -959,7 +975,7 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc;
     w.cand_stride = (long long)cand.size(); w.kp_stride = V.kp_cap;
     if (smem > 48 * 1024) ORBX_CUDA_L(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_octree<ORBX_QT_THREADS_LAT><<<dim3(1, 1), ORBX_QT_THREADS_LAT, smem, h->stream>>>(P, w);
+    k_octree<ORBX_QT_THREADS_LAT><<<dim3(1, 1), ORBX_QT_THREADS_LAT, smem, h->stream>>>(P, w, 0);
     h->total_launches += 1; h->stage_launches += 1;
     ORBX_CUDA_L(cudaGetLastError());
     int2 lc;

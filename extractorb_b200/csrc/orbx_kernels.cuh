@@ -489,6 +489,8 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
 // =================================================================================================
 #define ORBX_QT_THREADS 256      // large launch groups (throughput)
 #define ORBX_QT_THREADS_LAT 512  // small launch groups: one CTA per level is latency bound
+#define ORBX_QT_THREADS_BIG 1024 // levels of >= ORBX_QT_BIG_PIXELS pixels (tens of thousands of candidates per quadtree)
+#define ORBX_QT_BIG_PIXELS 1000000
 
 struct QtShared {
     short4* rect[2];  // x0, x1, y0, y1
@@ -549,12 +551,12 @@ __device__ int block_excl_scan(int* v, int n, int* scratch) {
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
-k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
+k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level_base) {
     extern __shared__ __align__(16) uint8_t smem_qt[];
     __shared__ int s_scratch[33];
     __shared__ int s_nexp, s_cut, s_state;
 
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int level = level_base + blockIdx.x, frame = blockIdx.y;
     const OrbxLevel& L = plan.lv[level];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int NC = plan.qt_nc;
