@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 __all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
-           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS"]
+           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
@@ -88,6 +88,7 @@ def load_library():
     L.orbx_frame_undistort_grid.argtypes = [vp, C.POINTER(FrameCalib), vp, i32, vp, vp, vp, C.POINTER(i32)]
     L.orbx_search_for_initialization.argtypes = [vp, C.POINTER(FrameCalib), vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, C.c_float, i32,
                                                  vp, C.POINTER(i32)]
+    L.orbx_clahe.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, C.c_double, i32, i32, vp, i32, sz, sz, vp]
     L.orbx_last_init_fallbacks.argtypes = [vp]
     L.orbx_stage_times.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.orbx_launch_count.restype = C.c_int64
@@ -338,3 +339,23 @@ def search_for_initialization(ext, calib, keys_un1, desc1, keys_un2, desc2, cell
                                                      d2.ctypes.data, len(k2), cs.ctypes.data, ci.ctypes.data, prev.ctypes.data, int(window),
                                                      float(nn_ratio), 1 if check_orientation else 0, m12.ctypes.data, C.byref(n)))
     return n.value, m12[:len(k1)].copy(), prev
+
+
+def clahe(ext, images, clip_limit=3.0, tiles=(8, 8)):
+    """cv::createCLAHE(clip_limit, Size(tiles[0], tiles[1]))->apply on one (h, w) or a stack (n, h, w) of uint8 host images
+    (the pre-processing step of the reference's demos, src/orb_extractor/main_orb_extractor.cpp:19-22), on the GPU."""
+    img = np.ascontiguousarray(images, np.uint8)
+    single = img.ndim == 2
+    a = img[None] if single else img
+    n, h, w = a.shape
+    out = np.empty_like(a)
+    ext._check(ext._L.orbx_clahe(ext._h, a.ctypes.data, MEM_HOST, n, w, h, w, w * h, float(clip_limit), int(tiles[0]), int(tiles[1]),
+                                 out.ctypes.data, MEM_HOST, w, w * h, None))
+    return out[0] if single else out
+
+
+def clahe_raw(ext, src_ptr, src_mem, n, w, h, row_stride, frame_stride, clip_limit, tiles, dst_ptr, dst_mem, dst_row_stride,
+              dst_frame_stride, stream=None):
+    """orbx_clahe on raw pointers (device- or host-resident frames)."""
+    ext._check(ext._L.orbx_clahe(ext._h, src_ptr, src_mem, n, w, h, row_stride, frame_stride, float(clip_limit), int(tiles[0]),
+                                 int(tiles[1]), dst_ptr, dst_mem, dst_row_stride, dst_frame_stride, stream))

@@ -5,6 +5,7 @@
 #include "../../include/ORBextractor.h"
 #include "../../include/ORBstereo.h"
 #include "../../include/ORBframe.h"
+#include "../../include/ORBclahe.h"
 
 #include <algorithm>
 #include <cmath>
@@ -198,6 +199,15 @@ int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vec
                                      reinterpret_cast<const OrbxKeyPoint*>(mvKeysRight.data()), dr.data(), Nr, mb, mbf,
                                      mvuRight.data(), mvDepth.data(), &kept);
     return rc == ORBX_OK ? kept : -1;
+}
+
+// ---- include/ORBclahe.h: cv::CLAHE::apply through the C-ABI ----
+bool ApplyCLAHE(ORBextractor& ext, const cv::Mat& src, cv::Mat& dst, double clipLimit, cv::Size tileGridSize) {
+    OrbxHandle* h = ext.NativeHandle();
+    if (!h || src.empty() || src.type() != CV_8UC1) return false;
+    dst.create(src.rows, src.cols, CV_8UC1);
+    return orbx_clahe(h, src.data, ORBX_MEM_HOST, 1, src.cols, src.rows, src.step, src.step * (size_t)src.rows, clipLimit, tileGridSize.width,
+                      tileGridSize.height, dst.data, ORBX_MEM_HOST, dst.step, dst.step * (size_t)dst.rows, nullptr) == ORBX_OK;
 }
 
 // ---- include/ORBframe.h: Frame post-processing and SearchForInitialization through the C-ABI ----

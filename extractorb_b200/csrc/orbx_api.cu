@@ -19,6 +19,7 @@
 #include "../../include/orbx.h"
 #include "orbx_kernels.cuh"
 #include "orbx_frame.cuh"
+#include "orbx_clahe.cuh"
 
 static const int8_t kPatternHost[1024] = {
 #include "orb_pattern.inc"
@@ -95,6 +96,7 @@ struct OrbxHandle {
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
     uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match / orbx_frame_* / orbx_search_for_initialization
+    uint8_t* d_clahe = nullptr; size_t d_clahe_bytes = 0;    // LUTs + staging of orbx_clahe
     int last_init_fallbacks = 0;                             // filtered re-enumerations of the last SearchForInitialization (diagnostic)
     // host-buffer pipeline: ORBX_IN_SLOTS input staging slots (the copy engine runs ahead of the two compute
     // streams), two output staging slots
@@ -719,7 +721,7 @@ void orbx_destroy(OrbxHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_plans(h);
-    cudaFree(h->d_stereo); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
+    cudaFree(h->d_stereo); cudaFree(h->d_clahe); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
     for (int i = 0; i < 4; ++i) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -1154,6 +1156,75 @@ int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, c
     ORBX_CUDA(cudaStreamSynchronize(st));
     if (n_matches) *n_matches = nm[0];
     h->last_init_fallbacks = nm[1];
+    return ORBX_OK;
+}
+
+// ---- CLAHE (orbx_clahe.cuh) ----
+int orbx_clahe(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height, size_t row_stride,
+               size_t frame_stride, double clip_limit, int tiles_x, int tiles_y, uint8_t* out, int out_mem, size_t out_row_stride,
+               size_t out_frame_stride, void* stream) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_frames < 0 || width <= 0 || height <= 0 || tiles_x <= 0 || tiles_y <= 0 || tiles_x > 64 || tiles_y > 4096 ||
+        (n_frames > 0 && (!images || !out)) || row_stride < (size_t)width || out_row_stride < (size_t)width ||
+        (n_frames > 1 && (frame_stride < row_stride * (size_t)(height - 1) + width || out_frame_stride < out_row_stride * (size_t)(height - 1) + width)))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad CLAHE arguments");
+    if (n_frames == 0) return ORBX_OK;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    // geometry exactly as cv::CLAHE::apply: extend to multiples of the tile grid (for the LUTs only)
+    int ew = width, eh = height;
+    if (!(width % tiles_x == 0 && height % tiles_y == 0)) { ew = width + (tiles_x - width % tiles_x); eh = height + (tiles_y - height % tiles_y); }
+    OrbxClaheArgs a;
+    a.w = width; a.h = height; a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tw = ew / tiles_x; a.th = eh / tiles_y;
+    const int area = a.tw * a.th;
+    a.lut_scale = (float)(256 - 1) / area;
+    a.clip = 0;
+    if (clip_limit > 0.0) a.clip = std::max((int)(clip_limit * area / 256), 1);
+    a.inv_tw = 1.0f / a.tw; a.inv_th = 1.0f / a.th;
+    // frames per launch group: input + output of a group stay in L2 between the two kernels
+    const size_t frame_bytes = (size_t)width * height;
+    int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, (40u << 20) / frame_bytes));
+    G = std::min(G, 65535);
+    const bool host_in = in_mem == ORBX_MEM_HOST, host_out = out_mem == ORBX_MEM_HOST;
+    const size_t lut_bytes = (size_t)G * tiles_x * tiles_y * 256;
+    const size_t o_lut = 0, o_in = align_up((long long)lut_bytes, 256), o_out = o_in + (host_in ? align_up((long long)(G * frame_bytes), 256) : 0);
+    const size_t need = o_out + (host_out ? align_up((long long)(G * frame_bytes), 256) : 0);
+    int rc = ensure_bytes(h, (void**)&h->d_clahe, &h->d_clahe_bytes, need, false);
+    if (rc != ORBX_OK) return rc;
+    a.lut = h->d_clahe + o_lut;
+    const size_t smem = (size_t)2 * tiles_x * 256;
+    if (smem > 48 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "too many tile columns");
+    for (int f0 = 0; f0 < n_frames; f0 += G) {
+        const int nf = std::min(G, n_frames - f0);
+        if (host_in) {
+            ORBX_CUDA(cudaMemcpy2DAsync(h->d_clahe + o_in, width, images + (size_t)f0 * frame_stride, row_stride, width,
+                                        frame_stride == row_stride * (size_t)height ? (size_t)height * nf : (size_t)height, cudaMemcpyHostToDevice, st));
+            if (frame_stride != row_stride * (size_t)height)
+                for (int f = 1; f < nf; ++f)
+                    ORBX_CUDA(cudaMemcpy2DAsync(h->d_clahe + o_in + (size_t)f * frame_bytes, width, images + (size_t)(f0 + f) * frame_stride, row_stride,
+                                                width, height, cudaMemcpyHostToDevice, st));
+            a.src = h->d_clahe + o_in; a.src_row = width; a.src_frame = (long long)frame_bytes;
+        } else {
+            a.src = images + (size_t)f0 * frame_stride; a.src_row = (long long)row_stride; a.src_frame = (long long)frame_stride;
+        }
+        if (host_out) { a.dst = h->d_clahe + o_out; a.dst_row = width; a.dst_frame = (long long)frame_bytes; }
+        else { a.dst = out + (size_t)f0 * out_frame_stride; a.dst_row = (long long)out_row_stride; a.dst_frame = (long long)out_frame_stride; }
+        k_clahe_lut<<<dim3(tiles_x * tiles_y, nf), 256, 0, st>>>(a);
+        k_clahe_apply<<<dim3(tiles_y + 1, nf), 256, smem, st>>>(a);
+        h->total_launches += 2; h->stage_launches += 2;
+        ORBX_CUDA(cudaGetLastError());
+        if (host_out) {
+            if (out_frame_stride == out_row_stride * (size_t)height)
+                ORBX_CUDA(cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_row_stride, h->d_clahe + o_out, width, width, (size_t)height * nf,
+                                            cudaMemcpyDeviceToHost, st));
+            else
+                for (int f = 0; f < nf; ++f)
+                    ORBX_CUDA(cudaMemcpy2DAsync(out + (size_t)(f0 + f) * out_frame_stride, out_row_stride, h->d_clahe + o_out + (size_t)f * frame_bytes, width,
+                                                width, height, cudaMemcpyDeviceToHost, st));
+        }
+        if ((host_in || host_out) && f0 + G < n_frames) ORBX_CUDA(cudaStreamSynchronize(st));   // staging buffers are reused by the next group
+    }
+    if (host_in || host_out) ORBX_CUDA(cudaStreamSynchronize(st));
     return ORBX_OK;
 }
 

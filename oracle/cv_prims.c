@@ -332,3 +332,83 @@ void ocv_undistort_points_f32(const float* xy_in, int n, float fxf, float fyf, f
         xy_out[2 * i + 1] = (float)(yy * ww);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CLAHE (OpenCV imgproc clahe.cpp: CLAHE_CalcLut_Body + CLAHE_Interpolation_Body, 8-bit path).
+ * Call sites: src/orb_extractor/main_orb_extractor.cpp:19-22, src/clahe/main_clahe.cpp:7-11.
+ * Pinned against cv2 4.13.0 (tests/test_clahe.py, tests/golden/clahe_kat.npz).
+ * ---------------------------------------------------------------------------------------------- */
+static int reflect101_idx(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+int ocv_clahe_u8(const uint8_t* src, int w, int h, size_t sstep, double clip_limit, int tilesX, int tilesY,
+                 uint8_t* dst, size_t dstep) {
+    if (!src || !dst || w <= 0 || h <= 0 || tilesX <= 0 || tilesY <= 0) return -1;
+    const int histSize = 256;
+    /* extended size for the LUTs (copyMakeBorder(..., 0, tilesY - rows % tilesY, 0, tilesX - cols % tilesX, REFLECT_101)) */
+    int ew = w, eh = h;
+    if (!(w % tilesX == 0 && h % tilesY == 0)) { ew = w + (tilesX - w % tilesX); eh = h + (tilesY - h % tilesY); }
+    const int tw = ew / tilesX, th = eh / tilesY;
+    const int tileSizeTotal = tw * th;
+    const float lutScale = (float)(histSize - 1) / tileSizeTotal;
+    int clipLimit = 0;
+    if (clip_limit > 0.0) {
+        clipLimit = (int)(clip_limit * tileSizeTotal / histSize);
+        if (clipLimit < 1) clipLimit = 1;
+    }
+    uint8_t* lut = (uint8_t*)malloc((size_t)tilesX * tilesY * histSize);
+    for (int k = 0; k < tilesX * tilesY; ++k) {
+        const int ty = k / tilesX, tx = k % tilesX;
+        int hist[256];
+        memset(hist, 0, sizeof(hist));
+        for (int y = ty * th; y < (ty + 1) * th; ++y) {
+            const uint8_t* row = src + (size_t)reflect101_idx(y, h) * sstep;
+            for (int x = tx * tw; x < (tx + 1) * tw; ++x) hist[row[reflect101_idx(x, w)]]++;
+        }
+        if (clipLimit > 0) {
+            int clipped = 0;
+            for (int i = 0; i < histSize; ++i)
+                if (hist[i] > clipLimit) { clipped += hist[i] - clipLimit; hist[i] = clipLimit; }
+            const int redistBatch = clipped / histSize;
+            int residual = clipped - redistBatch * histSize;
+            for (int i = 0; i < histSize; ++i) hist[i] += redistBatch;
+            if (residual != 0) {
+                const int residualStep = (histSize / residual) > 1 ? (histSize / residual) : 1;
+                for (int i = 0; i < histSize && residual > 0; i += residualStep, residual--) hist[i]++;
+            }
+        }
+        int sum = 0;
+        for (int i = 0; i < histSize; ++i) {
+            sum += hist[i];
+            int v = ocv_round_f((float)sum * lutScale);
+            lut[(size_t)k * histSize + i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
+    for (int y = 0; y < h; ++y) {
+        const float tyf = y * inv_th - 0.5f;
+        int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
+        const float ya = tyf - ty1, ya1 = 1.0f - ya;
+        if (ty1 < 0) ty1 = 0;
+        if (ty2 > tilesY - 1) ty2 = tilesY - 1;
+        const uint8_t* lutPlane1 = lut + (size_t)ty1 * tilesX * histSize;
+        const uint8_t* lutPlane2 = lut + (size_t)ty2 * tilesX * histSize;
+        for (int x = 0; x < w; ++x) {
+            const float txf = x * inv_tw - 0.5f;
+            int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
+            const float xa = txf - tx1, xa1 = 1.0f - xa;
+            if (tx1 < 0) tx1 = 0;
+            if (tx2 > tilesX - 1) tx2 = tilesX - 1;
+            const int srcVal = src[(size_t)y * sstep + x];
+            const int ind1 = tx1 * histSize + srcVal, ind2 = tx2 * histSize + srcVal;
+            const float res = (lutPlane1[ind1] * xa1 + lutPlane1[ind2] * xa) * ya1 + (lutPlane2[ind1] * xa1 + lutPlane2[ind2] * xa) * ya;
+            int v = ocv_round_f(res);
+            dst[(size_t)y * dstep + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(lut);
+    return 0;
+}

@@ -62,6 +62,14 @@ float ocv_fast_atan2(float y, float x);
 void ocv_undistort_points_f32(const float* xy_in, int n, float fx, float fy, float cx, float cy, const float* dist,
                               int n_dist, float* xy_out);
 
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply(src, dst) for CV_8UC1: per-tile clipped histograms ->
+ * LUTs, bilinear interpolation between the four surrounding tile LUTs in float (no FMA), round half to even.  Images
+ * whose sides are not multiples of the tile grid are extended with BORDER_REFLECT_101 for the LUTs only.  Call sites:
+ * src/orb_extractor/main_orb_extractor.cpp:19-22, src/clahe/main_clahe.cpp:7-11, main_show_clahe_keypoint.cpp:19-22.
+ * Returns 0, or -1 for bad arguments. */
+int ocv_clahe_u8(const uint8_t* src, int w, int h, size_t sstep, double clip_limit, int tiles_x, int tiles_y,
+                 uint8_t* dst, size_t dstep);
+
 #ifdef __cplusplus
 }
 #endif

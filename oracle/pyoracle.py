@@ -73,6 +73,8 @@ def lib():
         L.orb_oracle_search_for_initialization.restype = C.c_int
         L.orb_oracle_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.ocv_clahe_u8.restype = C.c_int
+        L.ocv_clahe_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.ocv_undistort_points_f32.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         L.ocv_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
         L.ocv_copy_make_border_reflect101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t,
@@ -235,6 +237,17 @@ def search_for_initialization(calib, kps_un1, desc1, kps_un2, desc2, start2, ite
                                                    len(k2), start2.ctypes.data, items2.ctypes.data, prev.ctypes.data, window, nn_ratio,
                                                    1 if check_orientation else 0, m12.ctypes.data)
     return n, m12[:len(k1)].copy(), prev
+
+
+def clahe(img, clip_limit=3.0, tiles=(8, 8)):
+    """cv::createCLAHE(clip_limit, Size(tiles[0], tiles[1]))->apply restated (oracle/cv_prims.c)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    rc = lib().ocv_clahe_u8(img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], float(clip_limit), int(tiles[0]), int(tiles[1]),
+                            out.ctypes.data, out.strides[0])
+    if rc != 0:
+        raise ValueError("bad CLAHE arguments")
+    return out
 
 
 # ----- the extractor --------------------------------------------------------------------------------

@@ -126,3 +126,25 @@ def random_frame_pair(seed, n1=1500, n2=1600, w=640, h=480):
     k1, d1 = make(n1)
     k2, d2 = make(n2)
     return k1, d1, k2, d2
+
+
+def clahe_cases(images):
+    """(name, image, clipLimit, tilesX, tilesY) for the CLAHE tests and their cv2 goldens (tests/golden/clahe_kat.npz)."""
+    rng = np.random.default_rng(77)
+    noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    low = (rng.integers(0, 40, (96, 120)) + 100).astype(np.uint8)
+    tiny = rng.integers(0, 256, (33, 47), dtype=np.uint8)
+    flat = np.full((64, 80), 117, np.uint8)
+    return [
+        ("robot866_3_8x8", images["robot866"], 3.0, 8, 8),           # the demos' call (main_orb_extractor.cpp:19-22)
+        ("luna_3_8x8", images["luna"], 3.0, 8, 8),
+        ("robot2196_40_8x8", images["robot2196"], 40.0, 8, 8),       # cv::createCLAHE() defaults
+        ("robot866_crop_2_4x6", images["robot866"][:477, :635].copy(), 2.0, 4, 6),   # sides not multiples of the grid
+        ("noise_3_8x8", noise, 3.0, 8, 8),
+        ("noise_0_8x8", noise, 0.0, 8, 8),                            # no clipping
+        ("low_3_8x8", low, 3.0, 8, 8),
+        ("low_3_16x3", low, 3.0, 16, 3),
+        ("tiny_3_8x8", tiny, 3.0, 8, 8),                              # 33x47: extended to 40x48, 6x5-pixel tiles
+        ("tiny_2_4x6", tiny, 2.0, 4, 6),
+        ("flat_3_8x8", flat, 3.0, 8, 8),                              # one histogram bin holds every pixel
+    ]
