@@ -1192,8 +1192,10 @@ int orbx_clahe(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, i
     int rc = ensure_bytes(h, (void**)&h->d_clahe, &h->d_clahe_bytes, need, false);
     if (rc != ORBX_OK) return rc;
     a.lut = h->d_clahe + o_lut;
-    const size_t smem = (size_t)2 * tiles_x * 256;
-    if (smem > 48 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "too many tile columns");
+    // two rows of tile LUTs + per-column interpolation terms (xa as float, two LUT bases as 16-bit halves)
+    const size_t smem = (size_t)2 * tiles_x * 256 + (size_t)((width + 3) & ~3) * 8;
+    if (width > 16384) return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "CLAHE: image wider than 16384 pixels");
+    if (smem > 48 * 1024) ORBX_CUDA(cudaFuncSetAttribute(k_clahe_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int f0 = 0; f0 < n_frames; f0 += G) {
         const int nf = std::min(G, n_frames - f0);
         if (host_in) {

@@ -129,36 +129,61 @@ k_clahe_apply(const OrbxClaheArgs a) {
         uint4* s = reinterpret_cast<uint4*>(s_lut);
         for (int i = tid; i < n16; i += 256) { s[i] = p1[i]; s[n16 + i] = p2[i]; }
     }
+    // per-column interpolation terms, once per CTA: xa = frac(x / tw - 0.5) and the two LUT bases (tile column * 256)
+    float* s_xa = reinterpret_cast<float*>(s_lut + 2 * a.tiles_x * 256);
+    uint32_t* s_xi = reinterpret_cast<uint32_t*>(s_xa + ((a.w + 3) & ~3));
+    for (int x = tid; x < a.w; x += 256) {
+        const float txf = __fsub_rn(__fmul_rn((float)x, a.inv_tw), 0.5f);
+        const int t1 = (int)floorf(txf);
+        s_xa[x] = __fsub_rn(txf, (float)t1);
+        s_xi[x] = (uint32_t)(max(t1, 0) * 256) | ((uint32_t)(min(t1 + 1, a.tiles_x - 1) * 256) << 16);
+    }
     __syncthreads();
     const uint8_t* plane1 = s_lut;
     const uint8_t* plane2 = s_lut + a.tiles_x * 256;
     const uint8_t* img = a.src + (long long)frame * a.src_frame;
     uint8_t* out = a.dst + (long long)frame * a.dst_frame;
     const bool words = (a.w & 3) == 0 && ((a.src_row | a.dst_row) & 3) == 0 && ((((uintptr_t)img) | ((uintptr_t)out)) & 3) == 0;
-    const int wq = words ? a.w >> 2 : a.w;                // work items per row
-    const int total = wq * (r1 - r0);
-    for (int i = tid; i < total; i += 256) {
-        const int rr = i / wq, c = i - rr * wq;
-        const int y = r0 + rr;
+    const int lane = tid & 31, wid = tid >> 5;
+    // u8 -> float without the conversion unit: 2^23 + b is exact, subtracting 2^23 leaves b
+    auto u8f = [](uint32_t b) { return __fsub_rn(__uint_as_float(0x4b000000u | b), 8388608.0f); };
+    for (int y = r0 + wid; y < r1; y += 8) {              // one warp per row
         const float tyf = __fsub_rn(__fmul_rn((float)y, a.inv_th), 0.5f);
         const float ya = __fsub_rn(tyf, (float)(band - 1)), ya1 = __fsub_rn(1.0f, ya);
-        const int npx = words ? 4 : 1;
-        const int xb = words ? 4 * c : c;
-        uint32_t v = words ? *reinterpret_cast<const uint32_t*>(img + (long long)y * a.src_row + xb) : img[(long long)y * a.src_row + xb];
-        uint32_t o = 0;
-        for (int k = 0; k < npx; ++k) {
-            const int x = xb + k;
-            const int sv = (v >> (8 * k)) & 0xffu;
-            const float txf = __fsub_rn(__fmul_rn((float)x, a.inv_tw), 0.5f);
-            const int t1 = (int)floorf(txf);
-            const float xa = __fsub_rn(txf, (float)t1), xa1 = __fsub_rn(1.0f, xa);
-            const int i1 = max(t1, 0) * 256 + sv, i2 = min(t1 + 1, a.tiles_x - 1) * 256 + sv;
-            const float top = __fadd_rn(__fmul_rn((float)plane1[i1], xa1), __fmul_rn((float)plane1[i2], xa));
-            const float bot = __fadd_rn(__fmul_rn((float)plane2[i1], xa1), __fmul_rn((float)plane2[i2], xa));
-            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-            o |= (uint32_t)min(max(__float2int_rn(res), 0), 255) << (8 * k);
+        const uint8_t* srow = img + (long long)y * a.src_row;
+        uint8_t* drow = out + (long long)y * a.dst_row;
+        if (words) {
+            for (int c = lane; c < (a.w >> 2); c += 32) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(srow + 4 * c);
+                const float4 xa4 = *reinterpret_cast<const float4*>(s_xa + 4 * c);
+                const uint4 xi4 = *reinterpret_cast<const uint4*>(s_xi + 4 * c);
+                const float xas[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
+                const uint32_t xis[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+                uint32_t o = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t sv = (v >> (8 * k)) & 0xffu;
+                    const uint32_t i1 = (xis[k] & 0xffffu) + sv, i2 = (xis[k] >> 16) + sv;
+                    const float xa = xas[k], xa1 = __fsub_rn(1.0f, xa);
+                    const float top = __fadd_rn(__fmul_rn(u8f(plane1[i1]), xa1), __fmul_rn(u8f(plane1[i2]), xa));
+                    const float bot = __fadd_rn(__fmul_rn(u8f(plane2[i1]), xa1), __fmul_rn(u8f(plane2[i2]), xa));
+                    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                    // round half to even through the 1.5 * 2^23 addition; res lies in [0, 255]
+                    o |= min(__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x1ffu, 255u) << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(drow + 4 * c) = o;
+            }
+        } else {
+            for (int x = lane; x < a.w; x += 32) {
+                const uint32_t sv = srow[x];
+                const uint32_t xi = s_xi[x];
+                const uint32_t i1 = (xi & 0xffffu) + sv, i2 = (xi >> 16) + sv;
+                const float xa = s_xa[x], xa1 = __fsub_rn(1.0f, xa);
+                const float top = __fadd_rn(__fmul_rn(u8f(plane1[i1]), xa1), __fmul_rn(u8f(plane1[i2]), xa));
+                const float bot = __fadd_rn(__fmul_rn(u8f(plane2[i1]), xa1), __fmul_rn(u8f(plane2[i2]), xa));
+                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                drow[x] = (uint8_t)min(__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x1ffu, 255u);
+            }
         }
-        if (words) *reinterpret_cast<uint32_t*>(out + (long long)y * a.dst_row + xb) = o;
-        else out[(long long)y * a.dst_row + xb] = (uint8_t)o;
     }
 }
