@@ -484,7 +484,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         {
             int max_rows = 0;
             for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
-            k_pyr_border<<<dim3((max_rows + 15) / 16, P.nlevels, nf), dim3(16, 16), 0, sb>>>(P, ws);
+            k_pyr_border<<<dim3((max_rows + ORBX_BORDER_ROWS - 1) / ORBX_BORDER_ROWS, P.nlevels, nf), dim3(16, 16), 0, sb>>>(P, ws);
             ++launches;
         }
         if (fork) {

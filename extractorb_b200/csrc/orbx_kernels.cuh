@@ -208,22 +208,39 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
 // (dx < 0) mirror level pixels -dx-3..-dx, for the right strip they mirror 2(w-1)-dx-3..2(w-1)-dx.  The word
 // that straddles level and border keeps its level bytes.  Band rows (the 19 rows above / below the level)
 // additionally copy the level columns from the reflected row.
+#define ORBX_BORDER_ROWS 64
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int level = blockIdx.y;
     const int frame = blockIdx.z;
     const OrbxLevel& L = plan.lv[level];
-    const int r = blockIdx.x * blockDim.y + threadIdx.y;
-    if (r >= L.plane_rows) return;
     const int lane = threadIdx.x;                              // 0..15
-    const bool band = r < ORBX_EDGE || r >= ORBX_EDGE + L.h;
     uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
+    // a CTA walks ORBX_BORDER_ROWS plane rows, 16 at a time (few, fatter CTAs: the kernel was bound by the CTA launch rate)
+    const int r_end = min((int)(blockIdx.x + 1) * ORBX_BORDER_ROWS, L.plane_rows);
+    for (int r = blockIdx.x * ORBX_BORDER_ROWS + threadIdx.y; r < r_end; r += 16) {
+    const bool band = r < ORBX_EDGE || r >= ORBX_EDGE + L.h;
     // level row this plane row mirrors (itself for middle rows), as words relative to level column 0
     const uint32_t* srow = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + reflect101(r - ORBX_EDGE, L.h)) * L.pitch + ORBX_PADL);
     uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)r * L.pitch + ORBX_PADL);   // word 0 = level column 0
     if (band) {
+        // level columns of a band row: 16-byte copies (level column 0 sits at plane byte 32 of a 64-byte aligned row), three
+        // independent loads in flight per lane before the stores, then the last words one by one
         const int nw = L.w >> 2;                               // words fully inside the level
-        for (int wx = lane; wx < nw; wx += 16) drow[wx] = srow[wx];
+        const int nv = L.w >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(srow);
+        uint4* d4 = reinterpret_cast<uint4*>(drow);
+        for (int base = lane; base < nv; base += 48) {
+            const bool h1 = base + 16 < nv, h2 = base + 32 < nv;
+            const uint4 t0 = s4[base];
+            uint4 t1 = t0, t2 = t0;
+            if (h1) t1 = s4[base + 16];
+            if (h2) t2 = s4[base + 32];
+            d4[base] = t0;
+            if (h1) d4[base + 16] = t1;
+            if (h2) d4[base + 32] = t2;
+        }
+        for (int wx = 4 * nv + lane; wx < nw; wx += 16) drow[wx] = srow[wx];
     }
     const int rw0 = L.w >> 2;                                  // first right-strip word (may straddle level/border)
     const int rwl = (L.w + ORBX_EDGE - 1) >> 2;                // last word holding border pixels
@@ -248,6 +265,7 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
             word = __byte_perm(orig, word, sel);
         }
         drow[wx] = word;
+    }
     }
 }
 
