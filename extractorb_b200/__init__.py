@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 __all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
-           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe"]
+           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe", "extract_frame"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
@@ -86,6 +86,8 @@ def load_library():
     L.orbx_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]
     L.orbx_frame_image_bounds.argtypes = [vp, C.POINTER(FrameCalib), i32, i32]
     L.orbx_frame_undistort_grid.argtypes = [vp, C.POINTER(FrameCalib), vp, i32, vp, vp, vp, C.POINTER(i32)]
+    L.orbx_extract_frame.argtypes = [vp, vp, i32, i32, sz, i32, i32, C.POINTER(FrameCalib), vp, vp, i32, C.POINTER(i32), C.POINTER(i32), vp, vp, vp,
+                                     C.POINTER(i32)]
     L.orbx_search_for_initialization.argtypes = [vp, C.POINTER(FrameCalib), vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, C.c_float, i32,
                                                  vp, C.POINTER(i32)]
     L.orbx_clahe.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, C.c_double, i32, i32, vp, i32, sz, sz, vp]
@@ -359,3 +361,21 @@ def clahe_raw(ext, src_ptr, src_mem, n, w, h, row_stride, frame_stride, clip_lim
     """orbx_clahe on raw pointers (device- or host-resident frames)."""
     ext._check(ext._L.orbx_clahe(ext._h, src_ptr, src_mem, n, w, h, row_stride, frame_stride, float(clip_limit), int(tiles[0]),
                                  int(tiles[1]), dst_ptr, dst_mem, dst_row_stride, dst_frame_stride, stream))
+
+
+def extract_frame(ext, image, calib, lapping=(0, 1000)):
+    """The monocular Frame constructor's use of one image (reference src/Frame.cc:307-347): ExtractORB + UndistortKeyPoints +
+    AssignFeaturesToGrid in one call, keypoints resident on the GPU in between.
+    -> (ret, mvKeys, mDescriptors, mvKeysUn, cell_start, cell_items)."""
+    img = np.ascontiguousarray(image, np.uint8)
+    h, w = img.shape
+    cap = ext.max_keypoints(w, h)
+    kps = np.zeros(cap, KP_DTYPE); un = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    start = np.zeros(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, np.int32)
+    items = np.zeros(cap, np.int32)
+    n, mono, placed = C.c_int(0), C.c_int(0), C.c_int(0)
+    ext._check(ext._L.orbx_extract_frame(ext._h, img.ctypes.data, w, h, img.strides[0], int(lapping[0]), int(lapping[1]), C.byref(calib),
+                                         kps.ctypes.data, desc.ctypes.data, cap, C.byref(n), C.byref(mono), un.ctypes.data, start.ctypes.data,
+                                         items.ctypes.data, C.byref(placed)))
+    return mono.value, kps[:n.value].copy(), desc[:n.value].copy(), un[:n.value].copy(), start, items[:placed.value].copy()

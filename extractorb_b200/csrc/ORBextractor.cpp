@@ -242,6 +242,37 @@ int UndistortAndAssignToGrid(ORBextractor& ext, const OrbxFrameCalib& calib, con
     return placed;
 }
 
+int ExtractFrame(ORBextractor& ext, const OrbxFrameCalib& calib, const cv::Mat& im, int x0, int x1, std::vector<cv::KeyPoint>& mvKeys,
+                 cv::Mat& mDescriptors, std::vector<cv::KeyPoint>& mvKeysUn, FrameGridCells& mGrid) {
+    OrbxHandle* h = ext.NativeHandle();
+    if (!h || im.empty() || im.type() != CV_8UC1) return -1;
+    const int cap = orbx_max_keypoints(h, im.cols, im.rows);
+    if (cap <= 0) return -1;
+    std::vector<OrbxKeyPoint> k((size_t)cap), u((size_t)cap);
+    std::vector<unsigned char> d((size_t)cap * 32);
+    std::vector<int32_t> start(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0), items((size_t)cap);
+    int n = 0, mono = 0, placed = 0;
+    if (orbx_extract_frame(h, im.data, im.cols, im.rows, im.step, x0, x1, &calib, k.data(), d.data(), cap, &n, &mono, u.data(), start.data(),
+                           items.data(), &placed) != ORBX_OK)
+        return -1;
+    static_assert(sizeof(cv::KeyPoint) == sizeof(OrbxKeyPoint), "cv::KeyPoint layout");
+    mvKeys.resize((size_t)n); mvKeysUn.resize((size_t)n);
+    if (n > 0) {
+        std::memcpy(mvKeys.data(), k.data(), (size_t)n * sizeof(OrbxKeyPoint));
+        std::memcpy(mvKeysUn.data(), u.data(), (size_t)n * sizeof(OrbxKeyPoint));
+        mDescriptors.create(n, 32, CV_8UC1);
+        for (int i = 0; i < n; ++i) std::memcpy(mDescriptors.ptr(i), &d[(size_t)i * 32], 32);
+    } else {
+        mDescriptors.release();
+    }
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+            const int c = i * FRAME_GRID_ROWS + j;
+            mGrid[i][j].assign(items.begin() + start[c], items.begin() + start[c + 1]);
+        }
+    return mono;
+}
+
 int SearchForInitialization(ORBextractor& ext, const OrbxFrameCalib& calib, const std::vector<cv::KeyPoint>& mvKeysUn1,
                             const cv::Mat& mDescriptors1, const std::vector<cv::KeyPoint>& mvKeysUn2, const cv::Mat& mDescriptors2,
                             const FrameGridCells& mGrid2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,

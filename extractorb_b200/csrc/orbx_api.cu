@@ -96,6 +96,9 @@ struct OrbxHandle {
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
     uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match / orbx_frame_* / orbx_search_for_initialization
+    uint8_t* d_frame = nullptr; size_t d_frame_bytes = 0;    // device-resident outputs of orbx_extract_frame
+    uint8_t* h_out1 = nullptr; size_t h_out1_bytes = 0;      // pinned read-back buffer of single-frame host calls
+    uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;    // pinned read-back buffer of orbx_extract_frame
     uint8_t* d_clahe = nullptr; size_t d_clahe_bytes = 0;    // LUTs + staging of orbx_clahe
     int last_init_fallbacks = 0;                             // filtered re-enumerations of the last SearchForInitialization (diagnostic)
     // host-buffer pipeline: ORBX_IN_SLOTS input staging slots (the copy engine runs ahead of the two compute
@@ -721,7 +724,7 @@ void orbx_destroy(OrbxHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_plans(h);
-    cudaFree(h->d_stereo); cudaFree(h->d_clahe); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
+    cudaFree(h->d_stereo); cudaFree(h->d_clahe); cudaFree(h->d_frame); if (h->h_frame) cudaFreeHost(h->h_frame); if (h->h_out1) cudaFreeHost(h->h_out1); cudaFree(h->d_pattern_f); cudaFree(h->d_angle_w); cudaFree(h->d_in); cudaFree(h->d_out);
     for (auto& e : h->events) for (auto& x : e.ev) cudaEventDestroy(x);
     for (int i = 0; i < 4; ++i) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -795,6 +798,8 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         const size_t out_slot = o_cnt_off + (size_t)align_up(8ll * group, 256);
         const int n_out_slots = n_frames > group ? 4 : 1;
         if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, (size_t)n_out_slots * out_slot, false); if (rc != ORBX_OK) return rc; }
+        const bool single_out = host_out && n_frames == 1;
+        if (single_out) { rc = ensure_bytes(h, (void**)&h->h_out1, &h->h_out1_bytes, out_slot, true); if (rc != ORBX_OK) return rc; }
         const int n_in_slots = n_frames > group ? 4 : 1;
         if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)n_in_slots * in_slot, false); if (rc != ORBX_OK) return rc; }
         int gi = 0;
@@ -841,9 +846,15 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                 ORBX_CUDA(cudaEventRecord(h->ev_done[oslot], cs));
                 if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
                 ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[oslot], 0));
-                if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
-                if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
-                if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
+                if (single_out) {
+                    // one frame: a single read-back into pinned memory; the caller's (usually pageable) arrays are filled after
+                    // the final synchronisation -- three copies into pageable memory would block the host one after the other
+                    ORBX_CUDA(cudaMemcpyAsync(h->h_out1, ob, out_slot, cudaMemcpyDeviceToHost, h->s_out));
+                } else {
+                    if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                    if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                    if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
+                }
                 ORBX_CUDA(cudaEventRecord(h->ev_d2h[oslot], h->s_out));
             } else {
                 rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set);
@@ -859,6 +870,14 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         if (rc != ORBX_OK) return rc;
         ORBX_CUDA(cudaStreamSynchronize(st));
         if (host_out) ORBX_CUDA(cudaStreamSynchronize(h->s_out));
+        if (single_out) {
+            int32_t c2[2];
+            std::memcpy(c2, h->h_out1 + o_cnt_off, 8);
+            const size_t nk = (size_t)std::min(std::max(c2[0], 0), cap_per_frame);     // entries beyond n are unspecified padding
+            if (kps) std::memcpy(kps, h->h_out1 + o_kps_off, nk * sizeof(OrbxKeyPoint));
+            if (desc) std::memcpy(desc, h->h_out1 + o_desc_off, nk * 32);
+            if (counts) std::memcpy(counts, c2, 8);
+        }
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
         bool overflow = false;
         rc = check_overflow(h, &overflow);
@@ -1088,7 +1107,7 @@ int orbx_frame_undistort_grid(OrbxHandle* h, const OrbxFrameCalib* calib, const 
     uint8_t* b = h->d_stereo;
     cudaStream_t st = h->stream;
     if (n > 0) ORBX_CUDA(cudaMemcpyAsync(b + o_k, keys, (size_t)n * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
-    k_frame_undistort_grid<<<1, 1024, 0, st>>>(*calib, (const OrbxKeyPoint*)(b + o_k), n, (OrbxKeyPoint*)(b + o_u), (int*)(b + o_c),
+    k_frame_undistort_grid<<<1, 1024, 0, st>>>(*calib, (const OrbxKeyPoint*)(b + o_k), n, nullptr, (OrbxKeyPoint*)(b + o_u), (int*)(b + o_c),
                                                (int*)(b + o_s), (int*)(b + o_i), (int*)(b + o_n));
     h->total_launches += 1; h->stage_launches += 1;
     ORBX_CUDA(cudaGetLastError());
@@ -1099,6 +1118,58 @@ int orbx_frame_undistort_grid(OrbxHandle* h, const OrbxFrameCalib* calib, const 
     ORBX_CUDA(cudaMemcpyAsync(&placed, b + o_n, 4, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     if (n_in_grid) *n_in_grid = placed;
+    return ORBX_OK;
+}
+
+// What the monocular Frame constructor does with one image (src/Frame.cc:307-347): ExtractORB, UndistortKeyPoints,
+// AssignFeaturesToGrid -- the keypoints stay on the device between the extraction and the grid kernel.
+int orbx_extract_frame(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                       const OrbxFrameCalib* calib, OrbxKeyPoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_out,
+                       OrbxKeyPoint* kps_un, int32_t* cell_start, int32_t* cell_items, int* n_in_grid) {
+    if (!h) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_out) *n_out = 0;
+    if (mono_out) *mono_out = 0;
+    if (n_in_grid) *n_in_grid = 0;
+    if (!calib_ok(calib, true) || capacity <= 0 || !kps || !desc || !kps_un || !cell_start || !cell_items)
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad frame arguments");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t cap = (size_t)capacity;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (size_t)align_up((long long)bytes, 256); return at; };
+    const size_t o_k = take(cap * sizeof(OrbxKeyPoint)), o_d = take(cap * 32), o_cnt = take(8), o_u = take(cap * sizeof(OrbxKeyPoint));
+    const size_t o_c = take(cap * 4), o_s = take((ORBX_GRID_CELLS + 1) * 4), o_i = take(cap * 4), o_n = take(4);
+    int rc = ensure_bytes(h, (void**)&h->d_frame, &h->d_frame_bytes, o, false);
+    if (rc != ORBX_OK) return rc;
+    uint8_t* b = h->d_frame;
+    rc = orbx_extract_batch(h, image, ORBX_MEM_HOST, 1, width, height, stride, stride * (size_t)height, lap0, lap1, (OrbxKeyPoint*)(b + o_k),
+                            b + o_d, capacity, (int32_t*)(b + o_cnt), ORBX_MEM_DEVICE, nullptr);
+    if (rc != ORBX_OK) return rc;
+    cudaStream_t st = h->stream;
+    k_frame_undistort_grid<<<1, 1024, 0, st>>>(*calib, (const OrbxKeyPoint*)(b + o_k), capacity, (const int*)(b + o_cnt), (OrbxKeyPoint*)(b + o_u),
+                                               (int*)(b + o_c), (int*)(b + o_s), (int*)(b + o_i), (int*)(b + o_n));
+    h->total_launches += 1; h->stage_launches += 1;
+    ORBX_CUDA(cudaGetLastError());
+    // one contiguous read-back into pinned memory (copies into pageable memory block the host one by one), then the
+    // `n` valid entries of each array are handed to the caller
+    rc = ensure_bytes(h, (void**)&h->h_frame, &h->h_frame_bytes, o, true);
+    if (rc != ORBX_OK) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_frame, b, o, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    const uint8_t* hb = h->h_frame;
+    int32_t cnt[2];
+    int placed = 0;
+    std::memcpy(cnt, hb + o_cnt, 8);
+    std::memcpy(&placed, hb + o_n, 4);
+    const size_t n = (size_t)std::min(std::max(cnt[0], 0), capacity);
+    std::memcpy(kps, hb + o_k, n * sizeof(OrbxKeyPoint));
+    std::memcpy(desc, hb + o_d, n * 32);
+    std::memcpy(kps_un, hb + o_u, n * sizeof(OrbxKeyPoint));
+    std::memcpy(cell_start, hb + o_s, (ORBX_GRID_CELLS + 1) * 4);
+    std::memcpy(cell_items, hb + o_i, (size_t)std::min(std::max(placed, 0), capacity) * 4);
+    if (n_out) *n_out = cnt[0];
+    if (mono_out) *mono_out = cnt[1];
+    if (n_in_grid) *n_in_grid = placed;
+    if (cnt[0] > capacity) return fail(h, ORBX_ERR_CAPACITY, "keypoint capacity too small");
     return ORBX_OK;
 }
 

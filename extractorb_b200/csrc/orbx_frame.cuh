@@ -81,8 +81,11 @@ __device__ __forceinline__ float grid_h_inv(const OrbxFrameCalib& c) { return __
 // cell in ascending keypoint index (the reference push_backs in index order).
 //   cell_start[ix * 48 + iy .. +1] delimit mGrid[ix][iy] inside cell_items.
 __global__ void __launch_bounds__(1024)
-k_frame_undistort_grid(const OrbxFrameCalib calib, const OrbxKeyPoint* __restrict__ keys, int n, OrbxKeyPoint* __restrict__ keys_un,
-                       int* __restrict__ cell_of, int* __restrict__ cell_start, int* __restrict__ cell_items, int* __restrict__ n_in_grid) {
+k_frame_undistort_grid(const OrbxFrameCalib calib, const OrbxKeyPoint* __restrict__ keys, int n, const int* __restrict__ n_dev,
+                       OrbxKeyPoint* __restrict__ keys_un, int* __restrict__ cell_of, int* __restrict__ cell_start,
+                       int* __restrict__ cell_items, int* __restrict__ n_in_grid) {
+    // n_dev: the keypoint count still lives on the device (the extraction that produced `keys` has not been read back)
+    if (n_dev) n = min(max(*n_dev, 0), n);
     __shared__ int s_cnt[ORBX_GRID_CELLS];
     __shared__ int s_start[ORBX_GRID_CELLS + 1];
     __shared__ int s_part[32];

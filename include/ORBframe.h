@@ -45,6 +45,12 @@ bool ComputeImageBounds(ORBextractor& ext, const cv::Mat& K, const cv::Mat& dist
 int UndistortAndAssignToGrid(ORBextractor& ext, const OrbxFrameCalib& calib, const std::vector<cv::KeyPoint>& mvKeys,
                              std::vector<cv::KeyPoint>& mvKeysUn, FrameGridCells& mGrid);
 
+// Frame::ExtractORB(0, im, x0, x1) + UndistortKeyPoints + AssignFeaturesToGrid in one call (what the monocular Frame constructor
+// does with its image, src/Frame.cc:307-347); the keypoints stay on the GPU between the extraction and the grid.  Returns the
+// extractor's return value (monoIndex), -1 on error.  Note: mvImagePyramid of `ext` is not refreshed by this call.
+int ExtractFrame(ORBextractor& ext, const OrbxFrameCalib& calib, const cv::Mat& im, int x0, int x1, std::vector<cv::KeyPoint>& mvKeys,
+                 cv::Mat& mDescriptors, std::vector<cv::KeyPoint>& mvKeysUn, FrameGridCells& mGrid);
+
 // Returns nmatches (or -1 on error); vnMatches12 is resized to mvKeysUn1.size(), vbPrevMatched updated in place.
 int SearchForInitialization(ORBextractor& ext, const OrbxFrameCalib& calib, const std::vector<cv::KeyPoint>& mvKeysUn1,
                             const cv::Mat& mDescriptors1, const std::vector<cv::KeyPoint>& mvKeysUn2, const cv::Mat& mDescriptors2,

@@ -166,6 +166,12 @@ ORBX_API int orbx_frame_image_bounds(OrbxHandle* h, OrbxFrameCalib* calib, int w
  * *n_in_grid = keypoints that fell inside the grid. */
 ORBX_API int orbx_frame_undistort_grid(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys, int n,
                                        OrbxKeyPoint* keys_un, int32_t* cell_start, int32_t* cell_items, int* n_in_grid);
+/* The monocular Frame constructor's use of one image in one call (src/Frame.cc:307-347): ExtractORB, UndistortKeyPoints,
+ * AssignFeaturesToGrid.  Same outputs as orbx_extract followed by orbx_frame_undistort_grid, but the keypoints stay on the
+ * device in between.  kps / desc / kps_un / cell_items need room for `capacity` entries (orbx_max_keypoints). */
+ORBX_API int orbx_extract_frame(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                                const OrbxFrameCalib* calib, OrbxKeyPoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_out,
+                                OrbxKeyPoint* kps_un, int32_t* cell_start, int32_t* cell_items, int* n_in_grid);
 /* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:705-814) with GetFeaturesInArea (src/Frame.cc:655-724),
  * DescriptorDistance (:2349-2365) and ComputeThreeMaxima (:2303-2344).  keys_un*, desc*: mvKeysUn / mDescriptors of
  * the two frames; cell_start2 / cell_items2: frame 2's grid from orbx_frame_undistort_grid; prev_matched: n1 (x, y)

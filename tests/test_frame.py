@@ -240,3 +240,28 @@ def test_gpu_frame_edge_cases(oracle, gpu_ext):
     bad = ex.FrameCalib()
     with pytest.raises(ex.OrbxError):
         ex.undistort_grid(ext, bad, k1)
+
+
+@pytest.mark.gpu
+def test_gpu_extract_frame_equals_separate_calls(oracle, gpu_ext):
+    """orbx_extract_frame (extraction + undistort + grid with the keypoints resident on the GPU) == orbx_extract followed by
+    orbx_frame_undistort_grid == the oracle chain, for a distorted and an undistorted camera and both lapping conventions."""
+    ex, _ = gpu_ext
+    for cam, seed, nf, lap in (("tum640", 3, 2000, (0, 1000)), ("euroc752", 11, 1200, (0, 0)), ("nodist640", 21, 1000, (100, 300))):
+        w, h, K, dist = FRAME_CAMERAS[cam]
+        img = synth_frame(seed, w, h)
+        ext = ex.ORBextractor(nf, 1.2, 8, 20, 7)
+        cal = ex.image_bounds(ext, *K, dist, w, h)
+        ret, kps, desc, un, start, items = ex.extract_frame(ext, img, cal, lap)
+        ret2, kps2, desc2 = ext(img, None, lap)
+        un2, start2, items2 = ex.undistort_grid(ext, cal, kps2)
+        assert ret == ret2 and kps.tobytes() == kps2.tobytes() and np.array_equal(desc, desc2)
+        assert un.tobytes() == un2.tobytes() and np.array_equal(start, start2) and np.array_equal(items, items2)
+        o = oracle.OracleExtractor(nf, 1.2, 8, 20, 7)
+        oret, okps, odesc = o.extract(img, lap)
+        ocal = oracle.make_calib(*K, dist, w, h)
+        oun = oracle.undistort_keypoints(ocal, okps)
+        ostart, oitems = oracle.assign_grid(ocal, oun)
+        assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+        assert un.tobytes() == oun.tobytes() and np.array_equal(start, ostart) and np.array_equal(items, oitems)
+        ext.close()

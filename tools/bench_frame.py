@@ -41,6 +41,18 @@ for name, cam, nf in (("752x480, 5000 features", "euroc752", 5000), ("640x480, 1
         if i >= 50:
             t_grid.append((t1 - t0) * 1e6)
             t_search.append((t2 - t1) * 1e6)
+    t_sep, t_fused = [], []
+    for i in range(250):
+        t0 = time.perf_counter()
+        _, ka, da = e(im2, None, (0, 1000))
+        ua, sa, ia = ex.undistort_grid(e, cal, ka)
+        t1 = time.perf_counter()
+        rb, kb, db, ub, sb, ib = ex.extract_frame(e, im2, cal, (0, 1000))
+        t2 = time.perf_counter()
+        if i >= 50:
+            t_sep.append((t1 - t0) * 1e6)
+            t_fused.append((t2 - t1) * 1e6)
+    assert kb.tobytes() == ka.tobytes() and ub.tobytes() == ua.tobytes() and np.array_equal(sb, sa) and np.array_equal(ib, ia)
     ocal = pyoracle.make_calib(*K, dist, w, h)
     c_grid, c_search = [], []
     for _ in range(20):
@@ -55,7 +67,8 @@ for name, cam, nf in (("752x480, 5000 features", "euroc752", 5000), ("640x480, 1
     assert ou2.tobytes() == u2.tobytes() and np.array_equal(os2, s2) and np.array_equal(oi2, i2)
     assert on == n and np.array_equal(om12, m12) and prev.tobytes() == oprev.tobytes()
     out[name] = {"keypoints": [int(len(k1)), int(len(k2))], "level0_keypoints_frame1": int((k1["octave"] == 0).sum()), "matches": int(n), "shortlist_fallbacks": int(e._L.orbx_last_init_fallbacks(e._h)),
-                 "undistort_grid_p50_us": float(np.median(t_grid)), "search_for_initialization_p50_us": float(np.median(t_search)),
+                 "undistort_grid_p50_us": float(np.median(t_grid)), "extract_then_grid_p50_us": float(np.median(t_sep)),
+                 "extract_frame_fused_p50_us": float(np.median(t_fused)), "search_for_initialization_p50_us": float(np.median(t_search)),
                  "cpu_oracle_undistort_grid_p50_us": float(np.median(c_grid)), "cpu_oracle_search_p50_us": float(np.median(c_search))}
     e.close()
 out["cpu"] = "oracle C restatement, 1 thread"
