@@ -54,7 +54,7 @@ struct PlanEntry {
                    desc == o.desc && cap == o.cap && counts == o.counts && fo == o.fo && stages == o.stages;
         }
     };
-    struct GraphSlot { GraphKey key; cudaGraphExec_t exec = nullptr; };
+    struct GraphSlot { GraphKey key; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
     GraphSlot graphs[4];
     int graph_next = 0;
 };
@@ -88,6 +88,9 @@ struct OrbxHandle {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_s2 = nullptr;
     cudaStream_t s_side = nullptr;      // side branch of captured graphs: border + blur run beside FAST + quadtree
+    // per-level branches of the single-frame graph: FAST + quadtree of level l start as soon as level l exists
+    cudaStream_t s_lvl[ORBX_MAX_LEVELS] = {};
+    cudaEvent_t ev_lvl_ready[ORBX_MAX_LEVELS] = {}, ev_lvl_done[ORBX_MAX_LEVELS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* d_pattern_f = nullptr;
     int2* d_angle_w = nullptr;
@@ -454,6 +457,25 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         ORBX_CUDA(cudaEventRecord(se->ev[0], st));
     }
     int64_t launches = 0;
+    // Single-frame graphs (one or two frames, everything captured): FAST and the quadtree of level l form their own branch
+    // that starts as soon as level l exists, instead of waiting for the whole pyramid -- level 0's quadtree is the longest
+    // kernel of a frame and now runs beside the resize cascade.
+    const bool per_level = in_capture && stages == STAGES_ALL && nf <= 2;
+    if (per_level) {
+        ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
+    }
+    auto level_branch = [&](int l) -> int {
+        const OrbxLevel& V = P.lv[l];
+        cudaStream_t sl = h->s_lvl[l];
+        ORBX_CUDA(cudaEventRecord(h->ev_lvl_ready[l], st));
+        ORBX_CUDA(cudaStreamWaitEvent(sl, h->ev_lvl_ready[l], 0));
+        k_fast_cells<<<dim3((V.ncells + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, sl>>>(P, ws, V.cell_off,
+                                                                                                                          V.cell_off + V.ncells);
+        k_octree<ORBX_QT_THREADS_BIG><<<dim3(1, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
+        launches += 2;
+        ORBX_CUDA(cudaEventRecord(h->ev_lvl_done[l], sl));
+        return ORBX_OK;
+    };
     if (stages & STAGES_PYRAMID) {
         {
             const OrbxLevel& V = P.lv[0];
@@ -462,6 +484,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             const int aligned16 = ((uintptr_t)d_imgs % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0) ? 1 : 0;
             k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride, aligned16);
             ++launches;
+            if (per_level) { const int rb = level_branch(0); if (rb != ORBX_OK) return rb; }
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const OrbxLevel& V = P.lv[l];
@@ -474,6 +497,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             else k_pyr_resize<false, 0><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             ++launches;
+            if (per_level) { const int rb = level_branch(l); if (rb != ORBX_OK) return rb; }
         }
         // In a captured graph the border fill and the blur form a side branch: neither FAST nor the quadtree
         // reads the border or the blurred levels, only k_describe (and pyramid downloads) do.
@@ -498,9 +522,15 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
     }
     const bool forked = in_capture && stages == STAGES_ALL;
     if (se) ORBX_CUDA(cudaEventRecord(se->ev[1], st));
-    if (stages & STAGES_KEYPOINTS) {
+    if (per_level) {
+        for (int l = 0; l < P.nlevels; ++l) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_lvl_done[l], 0));
+        ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        ++launches;
+    } else if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
-        k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws);
+        k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, 0, P.ncells_total);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
         // levels of a megapixel or more hold tens of thousands of candidates each: their quadtrees get 1024-thread CTAs
@@ -510,7 +540,8 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             ++launches;
         }
         if (nbig < P.nlevels) {
-            if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws, nbig);
+            if (nf <= 2) k_octree<ORBX_QT_THREADS_BIG><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, nbig);
+            else if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws, nbig);
             else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws, nbig);
             ++launches;
         }
@@ -551,12 +582,12 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     for (auto& g : pe->graphs)
         if (g.exec && g.key == key) {
             ORBX_CUDA(cudaGraphLaunch(g.exec, st));
-            const int64_t n = (stages & STAGES_PYRAMID ? pe->plan.nlevels + 1 : 0) + (stages & STAGES_KEYPOINTS ? 4 + (qt_big_levels(pe->plan) > 0 && qt_big_levels(pe->plan) < pe->plan.nlevels ? 1 : 0) : 0);
-            h->stage_launches += n; h->total_launches += n;
+            h->stage_launches += g.launches; h->total_launches += g.launches;
             h->cur = pe; h->resident_frames = nf; h->res_set = 0;
             return ORBX_OK;
         }
     cudaGraph_t graph = nullptr;
+    const int64_t launches_before = h->total_launches;
     ORBX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
                               frame_out0, stages, true);
@@ -573,6 +604,7 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { slot.exec = nullptr; return fail(h, ORBX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
     slot.key = key;
+    slot.launches = h->total_launches - launches_before;
     ORBX_CUDA(cudaGraphLaunch(slot.exec, st));
     return ORBX_OK;
 }
@@ -679,6 +711,11 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    for (int l = 0; l < prm->nlevels && l < ORBX_MAX_LEVELS && e == cudaSuccess; ++l) {
+        e = cudaStreamCreateWithFlags(&h->s_lvl[l], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_lvl_ready[l], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_lvl_done[l], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
@@ -737,6 +774,11 @@ void orbx_destroy(OrbxHandle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->s_side) cudaStreamDestroy(h->s_side);
+    for (int l = 0; l < ORBX_MAX_LEVELS; ++l) {
+        if (h->s_lvl[l]) cudaStreamDestroy(h->s_lvl[l]);
+        if (h->ev_lvl_ready[l]) cudaEventDestroy(h->ev_lvl_ready[l]);
+        if (h->ev_lvl_done[l]) cudaEventDestroy(h->ev_lvl_done[l]);
+    }
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);

@@ -310,12 +310,12 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ t, int p, i
 }
 
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32)
-k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
+k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int cell_base, const int cell_end) {
     extern __shared__ __align__(16) uint8_t smem_fast[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int ci = blockIdx.x * ORBX_FAST_WARPS + wib;
+    const int ci = cell_base + blockIdx.x * ORBX_FAST_WARPS + wib;     // [cell_base, cell_end): all cells, or one level's slice
     const int frame = blockIdx.y;
-    if (ci >= plan.ncells_total) return;
+    if (ci >= cell_end) return;
     OrbxCell cell;
     {
         const uint4* cp = reinterpret_cast<const uint4*>(ws.cells + ci);
