@@ -488,14 +488,22 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const OrbxLevel& V = P.lv[l];
-            const dim3 grd((V.w + ORBX_RS_TW - 1) / ORBX_RS_TW, (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nf);
+            const bool lat = nf <= 2;                                         // latency mode: 128x16 tiles
+            const int tile_h = lat ? ORBX_RS_TH_LAT : ORBX_RS_TH;
+            const dim3 grd((V.w + ORBX_RS_TW - 1) / ORBX_RS_TW, (V.h + tile_h - 1) / tile_h, nf);
             const bool area = pe->xtab[V.xtab_off].y == -1;
             const bool fixed = !area && pe->rs_pitch[l] <= ORBX_RS_PITCH;     // specialised instance: constant staging pitch
             const int pitch = fixed ? ORBX_RS_PITCH : pe->rs_pitch[l];
             const size_t smem = rs_smem_bytes(pe->rs_rows[l], pitch);
-            if (area) k_pyr_resize<true, 0><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-            else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-            else k_pyr_resize<false, 0><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+            if (lat) {
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+            } else {
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+            }
             ++launches;
             if (per_level) { const int rb = level_branch(l); if (rb != ORBX_OK) return rb; }
         }
@@ -643,9 +651,12 @@ int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
         rs = std::max(rs, rs_smem_bytes(pe->rs_rows[l], std::max(pe->rs_pitch[l], ORBX_RS_PITCH)));
     if (rs > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "scale factor too large for the resize kernel's shared memory");
     if (rs > 48 * 1024) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     return ORBX_OK;
 }

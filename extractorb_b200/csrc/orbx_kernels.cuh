@@ -59,6 +59,7 @@ k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8
 // AREA: exact 2x2 decimation, where OpenCV switches INTER_LINEAR to the INTER_AREA fast path.
 #define ORBX_RS_TW 128
 #define ORBX_RS_TH 64
+#define ORBX_RS_TH_LAT 16
 
 // Horizontal pass of one thread: destination column fixed, staged rows g, g+NG, ...  (NG = 0: run-time `ng`).
 // PITCH = 0: run-time staging pitch; otherwise the pitch is a constant and every load has an immediate offset.
@@ -87,7 +88,9 @@ __device__ __forceinline__ void rs_hpass(const uint8_t* __restrict__ q0, const u
 
 #define ORBX_RS_PITCH 192     // staging pitch of the specialised instance (covers scale factors up to ~1.25)
 
-template <bool AREA, int PITCH>
+// TH: tile height.  ORBX_RS_TH for throughput; ORBX_RS_TH_LAT for one or two frames, where a level is a handful of tiles and
+// the kernel time is one CTA's latency (more, smaller CTAs finish sooner).
+template <bool AREA, int PITCH, int TH>
 __global__ void __launch_bounds__(256)
 k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
     extern __shared__ __align__(16) uint8_t smem_rs[];
@@ -95,13 +98,13 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * ORBX_RS_TW, y0 = blockIdx.y * ORBX_RS_TH;
+    const int x0 = blockIdx.x * ORBX_RS_TW, y0 = blockIdx.y * TH;
     const int frame = blockIdx.z;
     uint8_t* fbase = ws.pyr + (long long)frame * ws.pyr_stride;
     const uint8_t* splane = fbase + S.plane_off;
     const int2* xtab = ws.xtab + L.xtab_off;
     const int2* ytab = ws.ytab + L.ytab_off;
-    const int tw = min(ORBX_RS_TW, L.w - x0), th = min(ORBX_RS_TH, L.h - y0);   // this tile's extent
+    const int tw = min(ORBX_RS_TW, L.w - x0), th = min(TH, L.h - y0);   // this tile's extent
     // source window (inclusive), second taps clamped into the level (their weight is 0 when clamped)
     const int sx_lo = __ldg(&xtab[x0]).x, sx_hi = min(__ldg(&xtab[x0 + tw - 1]).x + 1, S.w - 1);
     const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y0 + th - 1]).x + 1, S.h - 1);
