@@ -12,6 +12,7 @@
 #include "ORBExtractor.h"   // global-namespace spelling (reference inc/ORBExtractor.h), includes ORBextractor.h
 #include "ORBstereo.h"
 #include "ORBframe.h"
+#include "ORBclahe.h"
 
 static bool load_frames(const char* path, int& n, int& w, int& h, std::vector<uint8_t>& data) {
     FILE* fp = std::fopen(path, "rb");
@@ -68,6 +69,21 @@ int main(int argc, char** argv) {
         return 0;
     }
 
+    if (!std::strcmp(mode, "clahe")) {
+        // cv::createCLAHE(clip, Size(tx, ty))->apply on every frame (include/ORBclahe.h); argv[9] / argv[10] carry tx / ty,
+        // argv[5] the clip limit.  Output: the processed frames, w*h bytes each.
+        ORB_SLAM3::ORBextractor ex(nfeatures, 1.2f, nlevels, ini, mn);
+        std::fclose(out);
+        out = std::fopen(argv[3], "wb");
+        for (int i = 0; i < n; ++i) {
+            cv::Mat im(h, w, CV_8UC1, frames.data() + (size_t)i * w * h), res;
+            if (!ORB_SLAM3::ApplyCLAHE(ex, im, res, (double)scale, cv::Size(lap0, lap1))) { std::fprintf(stderr, "clahe: %s\n", ex.LastError().c_str()); return 13; }
+            for (int r = 0; r < h; ++r) std::fwrite(res.ptr(r), 1, (size_t)w, out);
+        }
+        std::fclose(out);
+        return 0;
+    }
+
     if (!std::strcmp(mode, "frame")) {
         // frames 0 / 1 = two views.  What the monocular Frame constructor does after ExtractORB (src/Frame.cc:307-347) and
         // Tracking::MonocularInitialization's matcher call (src/Tracking.cc: ORBmatcher matcher(0.9,true);
@@ -90,10 +106,16 @@ int main(int argc, char** argv) {
         std::vector<int> lap = {lap0, lap1};
         for (int k = 0; k < 2; ++k) {
             cv::Mat im(h, w, CV_8UC1, frames.data() + (size_t)k * w * h);
-            if (ex(im, cv::Mat(), keys[k], desc[k], lap) < 0) { std::fprintf(stderr, "frame: %s\n", ex.LastError().c_str()); return 8; }
-            desc[k] = desc[k].clone();
-            if (k == 0 && !ORB_SLAM3::ComputeImageBounds(ex, K, dist, w, h, calib)) return 9;
-            if (ORB_SLAM3::UndistortAndAssignToGrid(ex, calib, keys[k], un[k], grid[k]) < 0) return 10;
+            if (k == 0) {
+                // first frame: the three separate calls
+                if (ex(im, cv::Mat(), keys[k], desc[k], lap) < 0) { std::fprintf(stderr, "frame: %s\n", ex.LastError().c_str()); return 8; }
+                desc[k] = desc[k].clone();
+                if (!ORB_SLAM3::ComputeImageBounds(ex, K, dist, w, h, calib)) return 9;
+                if (ORB_SLAM3::UndistortAndAssignToGrid(ex, calib, keys[k], un[k], grid[k]) < 0) return 10;
+            } else {
+                // second frame: extraction + undistort + grid in one call (keypoints stay on the GPU in between)
+                if (ORB_SLAM3::ExtractFrame(ex, calib, im, lap0, lap1, keys[k], desc[k], un[k], grid[k]) < 0) return 12;
+            }
         }
         std::vector<cv::Point2f> prev(un[0].size());
         for (size_t i = 0; i < un[0].size(); ++i) prev[i] = un[0][i].pt;

@@ -138,3 +138,24 @@ def test_cpp_frame_matches_reference(demo, case):
         assert np.array_equal(out["cell_start" + k], g["cell_start" + k]) and np.array_equal(out["cell_items" + k], g["cell_items" + k])
     assert out["nmatches"] == int(g["nmatches_w100_o1"]) and np.array_equal(out["matches12"], g["matches12_w100_o1"])
     assert out["prev_matched"].tobytes() == g["prev_w100_o1"].tobytes()
+
+
+@pytest.mark.gpu
+def test_cpp_clahe_matches_cv2_golden(demo, images):
+    """include/ORBclahe.h: ORB_SLAM3::ApplyCLAHE(ext, image, out, 3.0, Size(8, 8)) against the cv2 golden (the demos' call,
+    reference src/orb_extractor/main_orb_extractor.cpp:19-22)."""
+    import zlib
+    from oracle import refio
+    with np.load(os.path.join(ROOT, "tests", "golden", "clahe_kat.npz")) as z:
+        crcs = {"robot866": int(z["crc_robot866_3_8x8"])}
+    frames = np.stack([images["robot866"], images["robot2196"]])
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.orbf"), os.path.join(td, "out.bin")
+        refio.write_frames(fin, frames)
+        # argv: run in out nfeatures <clip> nlevels ini min <tilesX> <tilesY> dump mode
+        r = subprocess.run([demo, "run", fin, fout, "1000", "3.0", "8", "20", "7", "8", "8", "0", "clahe"], capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stderr)
+        out = np.frombuffer(open(fout, "rb").read(), np.uint8).reshape(frames.shape)
+    assert zlib.crc32(out[0].tobytes()) == crcs["robot866"]
+    from oracle import pyoracle
+    assert np.array_equal(out[1], pyoracle.clahe(frames[1], 3.0, (8, 8)))
