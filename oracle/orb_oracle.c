@@ -415,6 +415,13 @@ int orb_oracle_extract(OrbOracle* o, const uint8_t* img, int w, int h, size_t st
     if (n_out) *n_out = 0;
     if (!img || w <= 0 || h <= 0) return -1;                                   /* :1083 */
     free_frame_state(o);
+    /* Geometry the reference cannot handle (a level without a single 30-px cell: division by zero at :794; levels of
+     * zero size: cv::resize asserts) is rejected before any pixel work -- the restatement must not loop on it either. */
+    for (int l = 0; l < o->nlevels; ++l) {
+        const int sw = ocv_round_f((float)w * o->inv_sf[l]), sh = ocv_round_f((float)h * o->inv_sf[l]);
+        const float width = (float)(sw - 2 * (EDGE_THRESHOLD - 3)), height = (float)(sh - 2 * (EDGE_THRESHOLD - 3));
+        if (sw < 1 || sh < 1 || (int)(width / (float)o->cell_w) < 1 || (int)(height / (float)o->cell_w) < 1) return -2;
+    }
     compute_pyramid(o, img, w, h, stride);                                     /* :1090 */
     int rc = compute_keypoints_octtree(o);                                     /* :1093 */
     if (rc < 0) return rc;
