@@ -843,8 +843,13 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
     __syncthreads();
     // ---- horizontal: item = (row pair, 4-pixel group); output x reads staged bytes x+13 .. x+19 ----
     const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+    // partial tiles (right / bottom edge of a level): horizontal sums nobody reads are not computed
+    const int xq_end = min(ORBX_BLUR_TW / 4, (L.blur_pitch - x0 + 3) >> 2);          // 4-pixel groups with an output column
+    const int rp_end = min(SROWS / 2, ((min(ORBX_BLUR_TH, L.h - y0) + 1) >> 1) + 3);   // row pairs feeding an output row
     for (int i = tid; i < (SROWS / 2) * (ORBX_BLUR_TW / 4); i += 256) {
         const int rp = i >> 5, xq = i & 31;
+        if (rp >= rp_end) break;
+        if (xq >= xq_end) continue;
         uint32_t h[2][4];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
