@@ -230,8 +230,21 @@ __device__ __forceinline__ void init_enumerate(const OrbxInitArgs& a, float x, f
     Top4 t;
     t.init();
     int running = 0;
-    for (int ix = minCX; ix <= maxCX; ++ix) {
-        const int s = __ldg(a.cell_start2 + ix * ORBX_GRID_ROWS + minCY), e = __ldg(a.cell_start2 + ix * ORBX_GRID_ROWS + maxCY + 1);
+    // the CSR ranges of all (at most 64) cell columns are fetched at once: lane c holds columns c and c + 32
+    const int ncol = maxCX - minCX + 1;
+    int cs0 = 0, ce0 = 0, cs1 = 0, ce1 = 0;
+    if (lane < ncol) {
+        cs0 = __ldg(a.cell_start2 + (minCX + lane) * ORBX_GRID_ROWS + minCY);
+        ce0 = __ldg(a.cell_start2 + (minCX + lane) * ORBX_GRID_ROWS + maxCY + 1);
+    }
+    if (lane + 32 < ncol) {
+        cs1 = __ldg(a.cell_start2 + (minCX + lane + 32) * ORBX_GRID_ROWS + minCY);
+        ce1 = __ldg(a.cell_start2 + (minCX + lane + 32) * ORBX_GRID_ROWS + maxCY + 1);
+    }
+    for (int c = 0; c < ncol; ++c) {
+        const int s0 = __shfl_sync(0xffffffffu, cs0, c & 31), e0 = __shfl_sync(0xffffffffu, ce0, c & 31);
+        const int s1 = __shfl_sync(0xffffffffu, cs1, c & 31), e1 = __shfl_sync(0xffffffffu, ce1, c & 31);
+        const int s = c < 32 ? s0 : s1, e = c < 32 ? e0 : e1;
         for (int base = s; base < e; base += 32) {
             const int p = base + lane;
             bool ok = false;
@@ -333,23 +346,29 @@ k_init_resolve(const OrbxInitArgs a) {
     __shared__ int s_scan[8];
     __shared__ int s_nact;
     {
-        const int per = (a.n1 + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int lo = min(tid * per, a.n1), hi = min(lo + per, a.n1);
-        int c = 0;
-        for (int i = lo; i < hi; ++i) c += (a.sl_count[i] > 0 && (int)(sl_key[(size_t)i * ORBX_SHORT_K] >> 22) <= ORBX_MATCH_TH_LOW) ? 1 : 0;
-        int inc = c;
+        // 256 consecutive keypoints per step (coalesced loads, four steps' loads in flight), ballot + warp totals give the rank
+        int total = 0;
+        for (int base = 0; base < a.n1; base += 4 * 256) {
+            bool f[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * 256 + tid;
+                f[j] = i < a.n1 && a.sl_count[i] > 0 && (int)(sl_key[(size_t)i * ORBX_SHORT_K] >> 22) <= ORBX_MATCH_TH_LOW;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned bal = __ballot_sync(0xffffffffu, f[j]);
+                if (lane == 0) s_scan[tid >> 5] = __popc(bal);
+                __syncthreads();
+                int off = total, all = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { const int c = s_scan[w]; all += c; if (w < (tid >> 5)) off += c; }
+                if (f[j]) a.act_list[off + __popc(bal & ((1u << lane) - 1u))] = base + j * 256 + tid;
+                total += all;
+                __syncthreads();
+            }
         }
-        if (lane == 31) s_scan[tid >> 5] = inc;
-        __syncthreads();
-        int off = inc - c;
-        for (int w = 0; w < (tid >> 5); ++w) off += s_scan[w];
-        if (tid == (int)blockDim.x - 1) s_nact = off + c;
-        for (int i = lo; i < hi; ++i)
-            if (a.sl_count[i] > 0 && (int)(sl_key[(size_t)i * ORBX_SHORT_K] >> 22) <= ORBX_MATCH_TH_LOW) a.act_list[off++] = i;
+        if (tid == 0) s_nact = total;
         __syncthreads();
     }
     const int nact = s_nact;
