@@ -23,6 +23,7 @@
 #define ORBX_GRID_CELLS (ORBX_GRID_COLS * ORBX_GRID_ROWS)
 #define ORBX_MATCH_TH_LOW 50        // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
 #define ORBX_MATCH_HISTO 30         // ORBmatcher::HISTO_LENGTH, :38
+#define ORBX_INIT_TAGS 2048
 #define ORBX_SHORT_K 8              // shortlist length per keypoint (two uint4 of keys, two of indices)
 
 // cv::undistortPoints for one point, K == P, no rectification: 5 fixed-point iterations (the default
@@ -331,13 +332,14 @@ k_init_resolve(const OrbxInitArgs a) {
     __shared__ int s_hist[ORBX_MATCH_HISTO];
     __shared__ int s_ind[3];
     __shared__ int s_nm;
-    __shared__ __align__(16) int s_mb[32];   // speculative bestIdx2 of each slot (-1: no match)
+    __shared__ int s_tag[ORBX_INIT_TAGS];    // bucket (candidate index mod ORBX_INIT_TAGS) -> lowest slot whose speculative match it holds (32: none)
     __shared__ unsigned s_pending;    // slots not resolved yet
     __shared__ int s_stop;            // first slot that clashes in this round (32: none)
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < a.n2; i += blockDim.x) { m21[i] = -1; vmd[i] = 0xffffu; }
     if (tid < ORBX_MATCH_HISTO) s_hist[tid] = 0;
     if (tid == 0) { s_nm = 0; s_pending = 0u; }
+    for (int i = tid; i < ORBX_INIT_TAGS; i += blockDim.x) s_tag[i] = 32;
     int n_fallback = 0;
     const int slot = tid >> 3, q = tid & 7, gl = lane & 24;
     const unsigned* sl_key = reinterpret_cast<const unsigned*>(a.sl_key);
@@ -435,22 +437,16 @@ k_init_resolve(const OrbxInitArgs a) {
             }
             const bool match = mine && bestIdx2 >= 0 && bestDist <= ORBX_MATCH_TH_LOW &&
                                (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio);                 // :758-760
-            if (q == 0) s_mb[slot] = match ? bestIdx2 : -1;
+            // every speculative match tags its candidate's bucket with its slot (lowest slot wins); two candidates sharing a
+            // bucket can only cause a spurious clash, i.e. one more round, never a missed one
+            if (q == 0 && match) atomicMin(&s_tag[bestIdx2 & (ORBX_INIT_TAGS - 1)], slot);
             if (tid == 0) s_stop = 32;
             __syncthreads();
-            // ---- clash detection ----
-            bool clash = dry && !first;
-            if (live && !first) {
-                // does an earlier slot's speculative match land on this live candidate?  (32 slots = 8 x int4)
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const int4 m = reinterpret_cast<const int4*>(s_mb)[v];
-                    clash = clash || (4 * v + 0 < slot && m.x == idx) || (4 * v + 1 < slot && m.y == idx) ||
-                            (4 * v + 2 < slot && m.z == idx) || (4 * v + 3 < slot && m.w == idx);
-                }
-            }
+            // ---- clash detection: did an earlier slot's speculative match land on this live candidate? ----
+            const bool clash = !first && (dry || (live && s_tag[idx & (ORBX_INIT_TAGS - 1)] < slot));
             if (clash) atomicMin(&s_stop, slot);
             __syncthreads();
+            if (q == 0 && match) s_tag[bestIdx2 & (ORBX_INIT_TAGS - 1)] = 32;             // all tags back to "none" for the next round
             // ---- apply the clash-free prefix ----
             const int stop = s_stop;
             if (mine && slot < stop && q == 0) {
