@@ -186,8 +186,9 @@ ORBX_API int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib*
 /* ----  the pre-processing step of the reference's demos: cv::createCLAHE(clip_limit,
  * Size(tiles_x, tiles_y))->apply(image, out) for CV_8UC1 (src/orb_extractor/main_orb_extractor.cpp:19-22,
  * src/clahe/main_clahe.cpp:7-11), on n_frames independent frames.  images / out live in in_mem / out_mem memory
- * (ORBX_MEM_*); strides in bytes; the two buffers must not overlap.  tiles_x <= 64.  `stream`: the cudaStream_t to launch on (NULL -> the handle's own); the call returns after
- * the results have landed when either side is host memory, and is asynchronous on `stream` otherwise. */
+ * (ORBX_MEM_*); strides in bytes; the two buffers must not overlap.  tiles_x <= 64, width <= 16384.  `stream`: the
+ * cudaStream_t to launch on (NULL -> the handle's own); the call returns after the results have landed when either side is
+ * host memory, and is asynchronous on `stream` otherwise. */
 ORBX_API int orbx_clahe(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height, size_t row_stride,
                         size_t frame_stride, double clip_limit, int tiles_x, int tiles_y, uint8_t* out, int out_mem,
                         size_t out_row_stride, size_t out_frame_stride, void* stream);
