@@ -5,7 +5,7 @@ runs for as long as asked).  Random image sizes / contents / constructor argumen
 every stage compared (pyramid planes with borders, FAST candidates, blurred levels, per-level keypoints) on a random
 subset.  Prints one line per failure and a summary; exit code 1 if anything differed.
 
-    python tools/fuzz_parity.py [--seconds 60] [--seed 0]
+    python tools/fuzz_parity.py [--seconds 60] [--seed 0] [--max-w 1400 --max-h 1000 --max-levels 10]
 """
 import argparse
 import os
@@ -24,6 +24,9 @@ from oracle import pyoracle  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=60.0)
 ap.add_argument("--seed", type=int, default=0)
+ap.add_argument("--max-w", type=int, default=1400)
+ap.add_argument("--max-h", type=int, default=1000)
+ap.add_argument("--max-levels", type=int, default=10)
 args = ap.parse_args()
 rng = np.random.default_rng(args.seed)
 with np.load(os.path.join(ROOT, "tests", "golden", "images.npz")) as z:
@@ -82,9 +85,9 @@ t0 = time.time()
 n_cases = n_fail = n_reject = 0
 while time.time() - t0 < args.seconds:
     scale = float(rng.choice([1.1, 1.2, 1.2, 1.2, 1.3, 1.5, 2.0]))
-    nl = int(rng.integers(1, 11))
-    w, h = int(rng.integers(70, 1400)), int(rng.integers(70, 1000))
-    nf = int(rng.integers(50, 4000))
+    nl = int(rng.integers(1, args.max_levels + 1))
+    w, h = int(rng.integers(70, args.max_w)), int(rng.integers(70, args.max_h))
+    nf = int(rng.integers(50, 4000 if args.max_w <= 1400 else 12000))
     ini, mn = int(rng.integers(8, 40)), int(rng.integers(3, 20))
     lap = [(0, 0), (0, 1000), (int(rng.integers(0, w)), int(rng.integers(0, 2 * w)))][rng.integers(0, 3)]
     img = random_image(w, h)
