@@ -1,8 +1,10 @@
+"""tools/e2e_probe.py -- which direction bounds the host-buffer pipeline: the same batch through orbx_extract_batch with device or
+pinned host memory on either side.  1024 frames (frame generation is CPU work: keep it short when several copies run at once)."""
 import sys, time, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 import torch, numpy as np
 import bench, extractorb_b200 as ex
-F=4096; W,H=bench.W,bench.H
+F=int(os.environ.get('PROBE_FRAMES', '1024')); W,H=bench.W,bench.H
 host=bench.make_frames(F,0).pin_memory(); dev=host.cuda()
 ext=ex.ORBextractor(1000,1.2,8,20,7,max_batch=256)
 cap=ext.max_keypoints(W,H)
