@@ -131,16 +131,18 @@ def test_live_reference_frame_if_present(oracle):
     from oracle import refio
     if not refio.have_ref_frame():
         pytest.skip("oracle/_ref/ref_frame not built (needs /root/reference)")
-    k1, d1, k2, d2 = random_frame_pair(11, 700, 650)
-    w, h, K, dist = FRAME_CAMERAS["euroc752"]
-    r = refio.run_reference_frame(w, h, *K, dist, k1, d1, k2, d2, 60, 0.9, True)
-    cal = oracle.make_calib(*K, dist, w, h)
-    u1, u2 = oracle.undistort_keypoints(cal, k1), oracle.undistort_keypoints(cal, k2)
-    assert u1.tobytes() == r["keys_un1"].tobytes() and u2.tobytes() == r["keys_un2"].tobytes()
-    s2, i2 = oracle.assign_grid(cal, u2)
-    assert np.array_equal(s2, r["cell_start2"]) and np.array_equal(i2, r["cell_items2"])
-    n, m12, prev = oracle.search_for_initialization(cal, u1, d1, u2, d2, s2, i2, None, 60, 0.9, True)
-    assert n == r["nmatches"] and np.array_equal(m12, r["matches12"]) and np.array_equal(bits(prev), bits(r["prev_matched"]))
+    for seed, n1, n2, cam, win, ratio, chk in ((11, 700, 650, "euroc752", 60, 0.9, True), (12, 2500, 1800, "tum640", 100, 0.9, True),
+                                               (13, 300, 4000, "nodist640", 10, 0.6, False), (14, 1200, 1, "euroc752", 300, 1.0, True)):
+        k1, d1, k2, d2 = random_frame_pair(seed, n1, n2)
+        w, h, K, dist = FRAME_CAMERAS[cam]
+        r = refio.run_reference_frame(w, h, *K, dist, k1, d1, k2, d2, win, ratio, chk)
+        cal = oracle.make_calib(*K, dist, w, h)
+        u1, u2 = oracle.undistort_keypoints(cal, k1), oracle.undistort_keypoints(cal, k2)
+        assert u1.tobytes() == r["keys_un1"].tobytes() and u2.tobytes() == r["keys_un2"].tobytes()
+        s2, i2 = oracle.assign_grid(cal, u2)
+        assert np.array_equal(s2, r["cell_start2"]) and np.array_equal(i2, r["cell_items2"])
+        n, m12, prev = oracle.search_for_initialization(cal, u1, d1, u2, d2, s2, i2, None, win, ratio, chk)
+        assert n == r["nmatches"] and np.array_equal(m12, r["matches12"]) and np.array_equal(bits(prev), bits(r["prev_matched"])), seed
 
 
 # ------------------------------------------------------------------------------------------------------ GPU
