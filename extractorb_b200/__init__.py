@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-__all__ = ["ORBextractor", "OrbxError", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
+__all__ = ["ORBextractor", "OrbxError", "OrbxParams", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
            "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe", "extract_frame"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -72,6 +72,7 @@ def load_library():
     L.orbx_destroy.argtypes = [vp]
     L.orbx_destroy.restype = None
     L.orbx_get_tables.argtypes = [vp] + [vp] * 6
+    L.orbx_ctor_tables.argtypes = [C.POINTER(OrbxParams)] + [vp] * 6
     L.orbx_max_keypoints.argtypes = [vp, i32, i32]
     L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, i32, i32, vp, vp, i32, vp, i32, vp]

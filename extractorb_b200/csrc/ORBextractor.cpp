@@ -28,14 +28,24 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
       mpHandle(nullptr), mnDevice(0), mbDownloadPyramid(true) {
     if (const char* env = std::getenv("ORBX_DEVICE")) mnDevice = std::atoi(env);
-    // The tables are plain host arithmetic; they are computed by the library's constructor code so that
-    // there is a single implementation, but a missing GPU must not make the constructor throw: ORB-SLAM3
-    // constructs extractors while parsing its settings (reference src/Tracking.cc:768-774).
-    mvScaleFactor.assign(nlevels > 0 ? nlevels : 0, 1.f);
+    // Constructor tables (reference :419-474): plain host arithmetic through the library's device-free entry point, so the
+    // accessors are right even when no GPU is present -- ORB-SLAM3 constructs extractors while parsing its settings
+    // (reference src/Tracking.cc:768-774) and copies the tables into every Frame (src/Frame.cc:97-103).  Only the
+    // handle (device state) is created lazily.
+    const size_t nl = (size_t)(nlevels > 0 ? nlevels : 0);
+    mvScaleFactor.assign(nl, 1.f);
     mvInvScaleFactor = mvLevelSigma2 = mvInvLevelSigma2 = mvScaleFactor;
-    mnFeaturesPerLevel.assign(mvScaleFactor.size(), 0);
+    mnFeaturesPerLevel.assign(nl, 0);
     umax.assign(16, 0);
-    mvImagePyramid.resize(mvScaleFactor.size());
+    mvImagePyramid.resize(nl);
+    {
+        OrbxParams prm;
+        std::memset(&prm, 0, sizeof(prm));
+        prm.nfeatures = nfeatures; prm.scale_factor = (float)scaleFactor; prm.nlevels = nlevels;
+        if (orbx_ctor_tables(&prm, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                             mnFeaturesPerLevel.data(), umax.data()) != ORBX_OK)
+            mLastError = "constructor arguments out of range (nlevels 1..16, scaleFactor > 1, nfeatures >= 0)";
+    }
     const cv::Point* p0 = nullptr;
     (void)p0;
     pattern.reserve(512);
@@ -71,8 +81,6 @@ bool ORBextractor::EnsureHandle() {
         mLastError = std::string("orbx_create: ") + orbx_status_string(rc);
         return false;
     }
-    orbx_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
-                    mnFeaturesPerLevel.data(), umax.data());
     mLastError.clear();
     return true;
 }

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -140,41 +141,54 @@ inline int qt_big_levels(const OrbxPlan& P) {
         }                                                                                            \
     } while (0)
 
-// ORBextractor::ORBextractor, :408-475.  Float/double mix reproduced literally.
-void build_ctor_tables(OrbxHandle* h) {
-    const int L = h->prm.nlevels;
-    const double scaleFactor = (double)h->prm.scale_factor;  // double member initialised from float (inc/ORBextractor.h:98)
-    h->sf.assign(L, 1.f); h->inv_sf.assign(L, 1.f); h->sigma2.assign(L, 1.f); h->inv_sigma2.assign(L, 1.f);
+// ORBextractor::ORBextractor, :408-475.  Float/double mix reproduced literally.  Pure host arithmetic: no CUDA call, so the
+// tables exist (orbx_ctor_tables) even where no device does.
+struct CtorTables {
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    int umax[16];
+};
+
+void compute_ctor_tables(int nfeatures, float scale_factor, int L, CtorTables& t) {
+    const double scaleFactor = (double)scale_factor;  // double member initialised from float (inc/ORBextractor.h:98)
+    t.sf.assign(L, 1.f); t.inv_sf.assign(L, 1.f); t.sigma2.assign(L, 1.f); t.inv_sigma2.assign(L, 1.f);
     for (int i = 1; i < L; ++i) {
-        h->sf[i] = (float)(h->sf[i - 1] * scaleFactor);
-        h->sigma2[i] = h->sf[i] * h->sf[i];
+        t.sf[i] = (float)(t.sf[i - 1] * scaleFactor);
+        t.sigma2[i] = t.sf[i] * t.sf[i];
     }
     for (int i = 0; i < L; ++i) {
-        h->inv_sf[i] = 1.0f / h->sf[i];
-        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+        t.inv_sf[i] = 1.0f / t.sf[i];
+        t.inv_sigma2[i] = 1.0f / t.sigma2[i];
     }
-    h->quota.assign(L, 0);
+    t.quota.assign(L, 0);
     float factor = (float)(1.0f / scaleFactor);
-    float nDesired = h->prm.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
     int sum = 0;
     for (int l = 0; l < L - 1; ++l) {
-        h->quota[l] = cv_round_f(nDesired);
-        sum += h->quota[l];
+        t.quota[l] = cv_round_f(nDesired);
+        sum += t.quota[l];
         nDesired *= factor;
     }
-    h->quota[L - 1] = std::max(h->prm.nfeatures - sum, 0);
+    if (L > 0) t.quota[L - 1] = std::max(nfeatures - sum, 0);
     // umax, :459-474
     int v, v0;
     const int vmax = cv_floor_f(ORBX_HALF_PATCH * sqrtf(2.f) / 2 + 1);
     const int vmin = cv_ceil_f(ORBX_HALF_PATCH * sqrtf(2.f) / 2);
     const double hp2 = ORBX_HALF_PATCH * ORBX_HALF_PATCH;
-    for (v = 0; v < 16; ++v) h->umax[v] = 0;
-    for (v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = 0; v < 16; ++v) t.umax[v] = 0;
+    for (v = 0; v <= vmax; ++v) t.umax[v] = cv_round_d(sqrt(hp2 - v * v));
     for (v = ORBX_HALF_PATCH, v0 = 0; v >= vmin; --v) {
-        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
-        h->umax[v] = v0;
+        while (t.umax[v0] == t.umax[v0 + 1]) ++v0;
+        t.umax[v] = v0;
         ++v0;
     }
+}
+
+void build_ctor_tables(OrbxHandle* h) {
+    CtorTables t;
+    compute_ctor_tables(h->prm.nfeatures, h->prm.scale_factor, h->prm.nlevels, t);
+    h->sf = t.sf; h->inv_sf = t.inv_sf; h->sigma2 = t.sigma2; h->inv_sigma2 = t.inv_sigma2; h->quota = t.quota;
+    for (int v = 0; v < 16; ++v) h->umax[v] = t.umax[v];
     // cv::fastAtan2 constants (float products, as OpenCV computes them) and factorPI (:104)
     const float s = (float)(180.0 / 3.1415926535897932384626433832795);
     h->fc.atan_p1 = 0.9997878412794807f * s;
@@ -445,6 +459,8 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
     OrbxPlan P = pe->plan;
     P.lap0 = lap0; P.lap1 = lap1;
     const OrbxWs& ws = set ? h->ws2 : h->ws;
+    if (nf < 1 || nf > (set ? h->ws2_frames : h->ws_frames) || h->ws_plan != pe)
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "internal: launch group larger than the workspace");
     const bool prof = (h->prm.flags & ORBX_FLAG_PROFILE) != 0 && !in_capture;
     StageEvents* se = nullptr;
     if (prof) {
@@ -581,8 +597,10 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
 // CUDA graph, captured once per argument set.  Large groups and profiled runs launch directly.
 int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
                  long long frame_stride, int nf, int lap0, int lap1, void* d_kps, uint8_t* d_desc, int cap_per_frame,
-                 int32_t* d_counts, int frame_out0, int stages, int set = 0) {
-    const bool use_graph = set == 0 && nf <= 8 && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_NO_GRAPH);
+                 int32_t* d_counts, int frame_out0, int stages, int set = 0, bool single_group = true) {
+    // Graphs pay only when the same argument set comes back (one frame / one small group per call).  The groups of a multi-group
+    // call differ in their image / output pointers, so each would be captured and instantiated anew: launched directly instead.
+    const bool use_graph = single_group && set == 0 && nf <= 8 && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_NO_GRAPH);
     if (!use_graph)
         return launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
                                 frame_out0, stages, false, set);
@@ -638,27 +656,47 @@ int ensure_bytes(OrbxHandle* h, void** p, size_t* have, size_t need, bool pinned
     return ORBX_OK;
 }
 
+// Dynamic shared memory limits.  cudaFuncSetAttribute is per function and per device, shared by every handle of the process:
+// two handles with different nfeatures / cell_size on different threads must not lower each other's limit between the call
+// and the launch (left / right / 5x-nfeatures init extractors coexist in ORB-SLAM3).  So every kernel that uses dynamic shared
+// memory gets the device's opt-in maximum (minus its static part) exactly once per device, under a process-wide mutex.
+template <typename K>
+cudaError_t raise_smem_limit(K kernel, int optin) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
+int set_kernel_attrs_device(OrbxHandle* h) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
+    if (h->device < 64 && done[h->device]) return ORBX_OK;
+    int optin = 0;
+    ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    ORBX_CUDA(raise_smem_limit(k_fast_cells, optin));
+    ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS>, optin));
+    ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_LAT>, optin));
+    ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_BIG>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, 0, ORBX_RS_TH>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<true, 0, ORBX_RS_TH>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, 0, ORBX_RS_TH_LAT>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<true, 0, ORBX_RS_TH_LAT>, optin));
+    ORBX_CUDA(raise_smem_limit(k_init_resolve, optin));
+    ORBX_CUDA(raise_smem_limit(k_clahe_apply, optin));
+    if (h->device < 64) done[h->device] = true;
+    return ORBX_OK;
+}
+
 int set_kernel_attrs(OrbxHandle* h, PlanEntry* pe) {
-    if (pe->fast_smem > 48 * 1024)
-        ORBX_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->fast_smem));
-    if (pe->qt_smem > 48 * 1024) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
-        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
-        ORBX_CUDA(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->qt_smem));
-    }
     size_t rs = 0;
     for (int l = 1; l < pe->plan.nlevels; ++l)
         rs = std::max(rs, rs_smem_bytes(pe->rs_rows[l], std::max(pe->rs_pitch[l], ORBX_RS_PITCH)));
     if (rs > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "scale factor too large for the resize kernel's shared memory");
-    if (rs > 48 * 1024) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0, ORBX_RS_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, 0, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-        ORBX_CUDA(cudaFuncSetAttribute(k_pyr_resize<true, 0, ORBX_RS_TH_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-    }
-    return ORBX_OK;
+    return set_kernel_attrs_device(h);
 }
 
 // Did any frame since the last check overflow its candidate workspace?  The flag word is fetched into pinned
@@ -667,10 +705,13 @@ int fetch_overflow(OrbxHandle* h, cudaStream_t st) {
     ORBX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     return ORBX_OK;
 }
-int check_overflow(OrbxHandle* h, bool* overflow) {
+int check_overflow(OrbxHandle* h, bool* overflow, cudaStream_t st) {
     const int flag = *h->h_flag;
     *overflow = (flag & 1) != 0;
-    if (flag) ORBX_CUDA(cudaMemset(h->ws.flags, 0, sizeof(int)));
+    if (flag) {   // cleared on the compute stream (ordered before the next launch there), then waited for: the caller may re-plan
+        ORBX_CUDA(cudaMemsetAsync(h->ws.flags, 0, sizeof(int), st));
+        ORBX_CUDA(cudaStreamSynchronize(st));
+    }
     return ORBX_OK;
 }
 
@@ -810,6 +851,22 @@ int orbx_get_tables(const OrbxHandle* h, float* scale, float* inv_scale, float* 
     return ORBX_OK;
 }
 
+int orbx_ctor_tables(const OrbxParams* prm, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl,
+                     int32_t* umax16) {
+    if (!prm || prm->nlevels < 1 || prm->nlevels > 64 || prm->nfeatures < 0 || !(prm->scale_factor > 1.0f))   // tables only: no ORBX_MAX_LEVELS limit
+        return ORBX_ERR_BAD_ARGUMENT;
+    CtorTables t;
+    compute_ctor_tables(prm->nfeatures, prm->scale_factor, prm->nlevels, t);
+    const size_t L = (size_t)prm->nlevels;
+    if (scale) memcpy(scale, t.sf.data(), L * sizeof(float));
+    if (inv_scale) memcpy(inv_scale, t.inv_sf.data(), L * sizeof(float));
+    if (sigma2) memcpy(sigma2, t.sigma2.data(), L * sizeof(float));
+    if (inv_sigma2) memcpy(inv_sigma2, t.inv_sigma2.data(), L * sizeof(float));
+    if (fpl) memcpy(fpl, t.quota.data(), L * sizeof(int32_t));
+    if (umax16) memcpy(umax16, t.umax, 16 * sizeof(int32_t));
+    return ORBX_OK;
+}
+
 int orbx_max_keypoints(const OrbxHandle* hc, int width, int height) {
     OrbxHandle* h = const_cast<OrbxHandle*>(hc);
     if (!h || width <= 0 || height <= 0) return ORBX_ERR_BAD_ARGUMENT;
@@ -865,7 +922,7 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                 const int remaining = n_frames - f0;
                 nf = std::min(nf, up);
                 if (remaining <= group) nf = std::min(nf, std::max(32, (remaining + 1) / 2));
-                if (remaining - nf < 16) nf = remaining;                        // do not leave a tiny tail group
+                if (remaining - nf < 16 && remaining <= group) nf = remaining;   // no tiny tail group -- but never more than the workspace holds
             }
             const int slot = gi & 1;
             const int set = dual ? slot : 0;
@@ -894,7 +951,7 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                 uint8_t* ob = (uint8_t*)h->d_out + (size_t)oslot * out_slot;
                 if (gi >= n_out_slots) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[oslot], 0));   // slot's previous results copied out
                 rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
-                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set);
+                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set, n_frames <= group);
                 if (rc != ORBX_OK) return rc;
                 ORBX_CUDA(cudaEventRecord(h->ev_done[oslot], cs));
                 if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
@@ -910,7 +967,7 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
                 }
                 ORBX_CUDA(cudaEventRecord(h->ev_d2h[oslot], h->s_out));
             } else {
-                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set);
+                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set, n_frames <= group);
                 if (rc != ORBX_OK) return rc;
                 if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
             }
@@ -933,7 +990,7 @@ int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_f
         }
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
         bool overflow = false;
-        rc = check_overflow(h, &overflow);
+        rc = check_overflow(h, &overflow, st);
         if (rc != ORBX_OK) return rc;
         if (!overflow) return ORBX_OK;
         // grow the candidate workspace and run the call again (every output is rewritten)
@@ -978,7 +1035,9 @@ static int run_stages_single(OrbxHandle* h, const uint8_t* image, int width, int
     rc = set_kernel_attrs(h, pe);
     if (rc != ORBX_OK) return rc;
     for (int attempt = 0;; ++attempt) {
-        rc = launch_group(h, pe, h->stream, h->d_in, width, (long long)width * height, 1, 0, 0, nullptr, nullptr, 0, nullptr, 0, stages);
+        // ComputeKeyPointsOctTree alone runs on the resident pyramid: the workspace set the last group left it in
+        const int set = (stages & STAGES_PYRAMID) ? 0 : h->res_set;
+        rc = launch_group(h, pe, h->stream, h->d_in, width, (long long)width * height, 1, 0, 0, nullptr, nullptr, 0, nullptr, 0, stages, set);
         if (rc != ORBX_OK) return rc;
         rc = fetch_overflow(h, h->stream);
         if (rc != ORBX_OK) return rc;
@@ -986,7 +1045,7 @@ static int run_stages_single(OrbxHandle* h, const uint8_t* image, int width, int
         if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
         if (!(stages & STAGES_KEYPOINTS)) return ORBX_OK;
         bool ov = false;
-        rc = check_overflow(h, &ov);
+        rc = check_overflow(h, &ov, h->stream);
         if (rc != ORBX_OK) return rc;
         if (!ov) return ORBX_OK;
         (void)attempt;
@@ -1015,10 +1074,16 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     if (nIni < 1) return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "aspect ratio < 0.5 (nIni == 0)");
     const int CM = (1 << ORBX_COORD_BITS) - 1;
     std::vector<uint2> cand((size_t)std::max(n, 1));
+    // Keys live in box coordinates, 0 <= x < max_x - min_x (the cell loop hands them over that way, :855-860).  A key
+    // outside the box would index past vpIniNodes in the reference (:574, undefined behaviour) and past the node table
+    // here: rejected up front, with the kernel's own float arithmetic for the initial-node index.
+    const float hX0 = (float)(max_x - min_x) / nIni;
     for (int i = 0; i < n; ++i) {
         const float x = keys[i].x, y = keys[i].y, r = keys[i].response;
         if (!(x >= 0 && x <= CM && y >= 0 && y <= CM && x == floorf(x) && y == floorf(y) && r >= 0 && r <= 255 && r == floorf(r)))
             return fail(h, ORBX_ERR_BAD_ARGUMENT, "DistributeOctTree keys must have integer coordinates in [0,4095] and integer responses in [0,255]");
+        if (!(x < (float)(max_x - min_x) && y <= (float)(max_y - min_y) && (int)(x / hX0) < nIni))
+            return fail(h, ORBX_ERR_BAD_ARGUMENT, "DistributeOctTree key outside the box [0, maxX-minX) x [0, maxY-minY]");
         cand[i] = make_uint2((uint32_t)x | ((uint32_t)y << ORBX_COORD_BITS) | ((uint32_t)r << 24), (uint32_t)i);
     }
     if (n >= (1 << 24)) return fail(h, ORBX_ERR_BAD_ARGUMENT, "too many keys");
@@ -1048,7 +1113,7 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     ORBX_CUDA_L(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc;
     w.cand_stride = (long long)cand.size(); w.kp_stride = V.kp_cap;
-    if (smem > 48 * 1024) ORBX_CUDA_L(cudaFuncSetAttribute(k_octree<ORBX_QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int ra = set_kernel_attrs_device(h); if (ra != ORBX_OK) { cleanup(); return ra; } }
     k_octree<ORBX_QT_THREADS_LAT><<<dim3(1, 1), ORBX_QT_THREADS_LAT, smem, h->stream>>>(P, w, 0);
     h->total_launches += 1; h->stage_launches += 1;
     ORBX_CUDA_L(cudaGetLastError());
@@ -1268,7 +1333,7 @@ int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, c
     a.sl_key = (uint4*)(b + o_sk); a.sl_idx = (uint4*)(b + o_si); a.sl_count = (int*)(b + o_sc);
     a.matches12 = (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.act_list = (int*)(b + o_al); a.n_matches = (int*)(b + o_n);
     const size_t smem = (size_t)m2 * 6 + 16;
-    if (smem > 48 * 1024) ORBX_CUDA(cudaFuncSetAttribute(k_init_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int ra = set_kernel_attrs_device(h); if (ra != ORBX_OK) return ra; }
     k_init_shortlist<<<(n1 + 7) / 8, 256, 0, st>>>(a);
     k_init_resolve<<<1, 256, smem, st>>>(a);
     h->total_launches += 2; h->stage_launches += 2;
@@ -1319,7 +1384,7 @@ int orbx_clahe(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, i
     // two rows of tile LUTs + per-column interpolation terms (xa as float, two LUT bases as 16-bit halves)
     const size_t smem = (size_t)2 * tiles_x * 256 + (size_t)((width + 3) & ~3) * 8;
     if (width > 16384) return fail(h, ORBX_ERR_IMAGE_TOO_LARGE, "CLAHE: image wider than 16384 pixels");
-    if (smem > 48 * 1024) ORBX_CUDA(cudaFuncSetAttribute(k_clahe_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int ra = set_kernel_attrs_device(h); if (ra != ORBX_OK) return ra; }
     for (int f0 = 0; f0 < n_frames; f0 += G) {
         const int nf = std::min(G, n_frames - f0);
         if (host_in) {

@@ -89,6 +89,11 @@ ORBX_API void orbx_destroy(OrbxHandle* h);
  * each), mnFeaturesPerLevel (nlevels ints), umax (16 ints).  Any pointer may be NULL. */
 ORBX_API int orbx_get_tables(const OrbxHandle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                     int32_t* features_per_level, int32_t* umax16);
+/* The same tables straight from the constructor arguments (nfeatures, scale_factor, nlevels of *params), computed on
+ * the host without touching CUDA: the reference builds them unconditionally in its constructor (ORBextractor.cc:419-474)
+ * and ORB-SLAM3 copies them into every Frame (src/Frame.cc:97-103), so they must exist even when no device does. */
+ORBX_API int orbx_ctor_tables(const OrbxParams* params, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                     int32_t* features_per_level, int32_t* umax16);
 /* Upper bound of keypoints one frame can yield (sum over levels of max(N_l + 2, 4 * nIni)). */
 ORBX_API int orbx_max_keypoints(const OrbxHandle* h, int width, int height);
 

@@ -175,7 +175,34 @@ static int cmd_bench(int argc, char** argv) {
     return 0;
 }
 
+// tables nfeatures scale nlevels ini min: the constructor tables of the unmodified class (ORBextractor.cc:419-474) through
+// its own accessors (inc/ORBextractor.h:63-83) and public members, one line of hex-exact numbers per table.
+static int cmd_tables(int argc, char** argv) {
+    if (argc < 7) return 2;
+    ORB_SLAM3::ORBextractor ex(std::atoi(argv[2]), (float)std::atof(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6]));
+    auto pf = [](const char* name, const std::vector<float>& v) {
+        std::printf("%s", name);
+        for (float f : v) { uint32_t u; std::memcpy(&u, &f, 4); std::printf(" %08x", u); }
+        std::printf("\n");
+    };
+    auto pi = [](const char* name, const std::vector<int>& v) {
+        std::printf("%s", name);
+        for (int i : v) std::printf(" %d", i);
+        std::printf("\n");
+    };
+    std::printf("levels %d\n", ex.GetLevels());
+    { float f = ex.GetScaleFactor(); uint32_t u; std::memcpy(&u, &f, 4); std::printf("scaleFactor %08x\n", u); }
+    pf("mvScaleFactor", ex.GetScaleFactors());
+    pf("mvInvScaleFactor", ex.GetInverseScaleFactors());
+    pf("mvLevelSigma2", ex.GetScaleSigmaSquares());
+    pf("mvInvLevelSigma2", ex.GetInverseScaleSigmaSquares());
+    pi("mnFeaturesPerLevel", ex.mnFeaturesPerLevel);
+    pi("umax", ex.umax);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "tables")) return cmd_tables(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "run")) return cmd_run(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "bench")) return cmd_bench(argc, argv);
     std::fprintf(stderr,

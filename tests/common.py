@@ -148,3 +148,24 @@ def clahe_cases(images):
         ("tiny_2_4x6", tiny, 2.0, 4, 6),
         ("flat_3_8x8", flat, 3.0, 8, 8),                              # one histogram bin holds every pixel
     ]
+
+
+# (nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) for the constructor-table parity test: BASELINE.json's configs,
+# the demos' 5 * 1500, other scales / level counts, and degenerate quotas
+CTOR_TABLE_CASES = [
+    (1000, 1.2, 8, 20, 7), (1200, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (8000, 1.2, 12, 20, 7), (7500, 1.2, 8, 20, 7),
+    (1500, 1.2, 8, 20, 7), (500, 1.5, 5, 25, 10), (1200, 2.0, 3, 20, 7), (1000, 1.1, 10, 15, 5), (20000, 1.2, 8, 20, 7),
+    (1, 1.2, 8, 20, 7), (0, 1.2, 1, 20, 7), (300, 1.3, 16, 20, 7), (1000, 1.01, 4, 20, 7),
+]
+
+
+def parse_tables(text):
+    """Output of `ref_extract tables` / `dropin_main tables`: name followed by hex float bit patterns or ints."""
+    out = {}
+    for line in text.strip().splitlines():
+        name, *vals = line.split()
+        if name in ("mnFeaturesPerLevel", "umax", "levels"):
+            out[name] = [int(v) for v in vals]
+        else:
+            out[name] = [int(v, 16) for v in vals]      # float bit patterns: compared exactly
+    return out

@@ -2,6 +2,8 @@
 // unmodified reference (same frame / result file formats), so that tests/test_cpp_dropin.py can compare the
 // two programs' outputs byte for byte.  Also exercises the accessors, the stage-wise public methods and the
 // two-thread stereo pattern of the reference's caller (src/Frame.cc:109-112).
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +28,72 @@ static bool load_frames(const char* path, int& n, int& w, int& h, std::vector<ui
     return ok;
 }
 
+// tables nfeatures scale nlevels ini min: the constructor tables through the class's accessors and public members, in the
+// format of `oracle/_ref/ref_extract tables` (reference inc/ORBextractor.h:63-83).  Needs no GPU: the tables are host arithmetic.
+static int cmd_tables(int argc, char** argv) {
+    if (argc < 7) return 2;
+    ORB_SLAM3::ORBextractor ex(std::atoi(argv[2]), (float)std::atof(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6]));
+    auto pf = [](const char* name, const std::vector<float>& v) {
+        std::printf("%s", name);
+        for (size_t i = 0; i < v.size(); ++i) { uint32_t u; std::memcpy(&u, &v[i], 4); std::printf(" %08x", u); }
+        std::printf("\n");
+    };
+    auto pi = [](const char* name, const std::vector<int>& v) {
+        std::printf("%s", name);
+        for (size_t i = 0; i < v.size(); ++i) std::printf(" %d", v[i]);
+        std::printf("\n");
+    };
+    std::printf("levels %d\n", ex.GetLevels());
+    { float f = ex.GetScaleFactor(); uint32_t u; std::memcpy(&u, &f, 4); std::printf("scaleFactor %08x\n", u); }
+    pf("mvScaleFactor", ex.GetScaleFactors());
+    pf("mvInvScaleFactor", ex.GetInverseScaleFactors());
+    pf("mvLevelSigma2", ex.GetScaleSigmaSquares());
+    pf("mvInvLevelSigma2", ex.GetInverseScaleSigmaSquares());
+    pi("mnFeaturesPerLevel", ex.mnFeaturesPerLevel);
+    pi("umax", ex.umax);
+    return 0;
+}
+
+// latency <frames.orbf> iters nfeatures scale nlevels ini min: wall-clock latency of the drop-in operator() itself (what a
+// Frame constructor pays, reference src/Frame.cc:419-427) -- 5- and 6-argument overloads, with and without the download of
+// mvImagePyramid.  Prints one JSON object (microseconds).
+static int cmd_latency(int argc, char** argv) {
+    if (argc < 9) return 2;
+    int n, w, h;
+    std::vector<uint8_t> frames;
+    if (!load_frames(argv[2], n, w, h, frames)) { std::fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    const int iters = std::atoi(argv[3]);
+    ORB_SLAM3::ORBextractor ex(std::atoi(argv[4]), (float)std::atof(argv[5]), std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]));
+    std::printf("{\"width\": %d, \"height\": %d, \"iters\": %d", w, h, iters);
+    const char* names[4] = {"five_arg_with_pyramid", "five_arg_no_pyramid", "six_arg_with_pyramid", "six_arg_no_pyramid"};
+    for (int mode = 0; mode < 4; ++mode) {
+        ex.SetPyramidDownload((mode & 1) == 0);
+        std::vector<double> us;
+        size_t nk = 0;
+        for (int it = 0; it < iters + 20; ++it) {
+            cv::Mat img(h, w, CV_8UC1, frames.data() + (size_t)(it % n) * w * h);
+            std::vector<cv::KeyPoint> kps;
+            cv::Mat desc;
+            std::vector<int> lap = {0, 0};
+            std::vector<std::vector<cv::KeyPoint> > lvl;
+            const auto t0 = std::chrono::steady_clock::now();
+            const int ret = mode < 2 ? ex(img, cv::Mat(), kps, desc, lap) : ex(img, cv::Mat(), kps, desc, lap, lvl);
+            const auto t1 = std::chrono::steady_clock::now();
+            if (ret < 0) { std::fprintf(stderr, "latency: %s\n", ex.LastError().c_str()); return 3; }
+            if (it >= 20) us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+            nk = kps.size();
+        }
+        std::sort(us.begin(), us.end());
+        std::printf(", \"%s\": {\"p50_us\": %.2f, \"p99_us\": %.2f, \"keypoints\": %zu}", names[mode], us[us.size() / 2],
+                    us[std::min(us.size() - 1, (size_t)(us.size() * 0.99))], nk);
+    }
+    std::printf("}\n");
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "tables")) return cmd_tables(argc, argv);
+    if (argc >= 2 && !std::strcmp(argv[1], "latency")) return cmd_latency(argc, argv);
     if (argc < 12 || std::strcmp(argv[1], "run")) {
         std::fprintf(stderr, "usage: %s run <frames.orbf> <out.orbr> nfeatures scale nlevels ini min lap0 lap1 dump_pyr [mode]\n", argv[0]);
         return 2;

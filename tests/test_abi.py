@@ -120,3 +120,26 @@ int main(int argc, char**) {
                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_sources_parse_against_opencv_api(tmp_path):
+    """The non-compat branch of include/orbx_cv_compat.hpp (`__has_include(<opencv2/core.hpp>)`): every header of include/, the
+    host side of the drop-in class and its test driver are parsed against declarations spelled like the public OpenCV core API
+    (tests/cpp/opencv_stub; this image has no OpenCV C++ headers).  Catches uses of cv:: types that only the compat layer offers."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("g++ not available")
+    inc, stub = os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "opencv_stub")
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('#include "orbx_cv_compat.hpp"\n#ifndef ORBX_HAVE_OPENCV\n#error "compat layer active: the stub was not picked up"\n#endif\n'
+                     '#ifndef OPENCV_CORE_HPP_STUB\n#error "stub header not included"\n#endif\nint main() { return 0; }\n')
+    srcs = [str(probe), os.path.join(ROOT, "extractorb_b200", "csrc", "ORBextractor.cpp"), os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp")]
+    for hdr in ("ORBextractor.h", "ORBExtractor.h", "ORBstereo.h", "ORBframe.h", "ORBclahe.h"):
+        tu = tmp_path / ("cv_%s.cpp" % hdr.replace(".", "_"))
+        tu.write_text('#include "%s"\nint main() { return 0; }\n' % hdr)
+        srcs.append(str(tu))
+    for src in srcs:
+        r = subprocess.run([cxx, "-std=c++11", "-Wall", "-I", stub, "-I", inc, "-fsyntax-only", src], capture_output=True, text=True)
+        assert r.returncode == 0, (src, r.stderr)
