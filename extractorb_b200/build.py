@@ -38,7 +38,7 @@ def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "orbx.h")]
     if not force and not _stale(LIB, srcs):
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB, os.path.join(CSRC, "orbx_api.cu")]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB, os.path.join(CSRC, "orbx_api.cu"), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -4,6 +4,7 @@
 // Reference being replaced: ORB_SLAM3::ORBextractor (/root/reference/src/orb_extractor/ORBextractor.cc,
 // twin ORBExtractor.cpp).  Line citations below refer to ORBextractor.cc.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a pointer test when no profiler is attached
 
 #include <cfloat>
 #include <cstdint>
@@ -38,6 +39,9 @@ struct PlanEntry {
     OrbxPlan plan;
     std::vector<int2> xtab, ytab;
     std::vector<OrbxCell> cells;
+    std::vector<OrbxFastTile> tiles;
+    OrbxFastTile* d_tiles = nullptr;
+    size_t ft_smem = 0;
     int2* d_xtab = nullptr;
     int2* d_ytab = nullptr;
     OrbxCell* d_cells = nullptr;
@@ -47,6 +51,8 @@ struct PlanEntry {
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
+    int rs_split_x[ORBX_MAX_LEVELS] = {0};  // extent of the second-to-last tile when the last two share the remainder, else 0
+    int rs_split_y[ORBX_MAX_LEVELS] = {0};
     // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
     struct GraphKey {
         const void* imgs; long long rs, fs; int nf, lap0, lap1; void* kps; void* desc; int cap; void* counts; int fo, stages;
@@ -75,6 +81,7 @@ struct OrbxHandle {
     int umax[16];
     OrbxFloatConsts fc;
     int cand_per_cell = 64;
+    bool fast_v1 = false;          // ORBX_FAST_V1=1: the round-1 warp-per-cell FAST kernel (A/B measurements only)
     // plans keyed by image size
     std::map<std::pair<int, int>, PlanEntry*> plans;
     PlanEntry* cur = nullptr;      // plan of the resident frames
@@ -214,10 +221,26 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
     }
 }
 
+// Host twins of rs_tile_span (orbx_kernels.cuh): the resize kernel's tile grid along one axis.
+int rs_axis_split(int len, int full, int align) {
+    const int nb = (len + full - 1) / full, rem = len % full;
+    if (nb < 2 || rem == 0 || rem >= ORBX_RS_MIN_EDGE) return 0;
+    const int left = len - (nb - 2) * full;                   // what the last two tiles share: full + rem
+    return (int)align_up((left + 1) / 2, align);
+}
+void rs_host_span(int b, int nb, int full, int len, int split, int& o, int& n) {
+    o = b * full;
+    n = std::min(full, len - o);
+    if (split > 0) {
+        if (b == nb - 2) n = split;
+        else if (b == nb - 1) { o = (nb - 2) * full + split; n = len - o; }
+    }
+}
+
 void free_plan(PlanEntry* p) {
     if (!p) return;
     for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_blur_tiles);
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_tiles); cudaFree(p->d_blur_tiles);
     delete p;
 }
 
@@ -232,7 +255,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.min_th = std::min(std::max(h->prm.min_th_fast, 0), 255);
     for (int i = 0; i < 16; ++i) P.umax[i] = h->umax[i];
     long long plane_off = 0, blur_off = 0, cand_off = 0;
-    int kp_off = 0, maxcw = 7, maxch = 7, qt_nc = 8;
+    int kp_off = 0, maxcw = 7, maxch = 7, qt_nc = 8, ft_maxtw = 7, ft_maxth = 7, ft_qcap = 1;
     for (int l = 0; l < L; ++l) {
         OrbxLevel& V = P.lv[l];
         V.w = cv_round_f((float)width * h->inv_sf[l]);     // :1171
@@ -257,15 +280,23 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 linear_axis_table(S.w, V.w, pe->xtab);
                 linear_axis_table(S.h, V.h, pe->ytab);
             }
-            // shared-memory window of the resize kernel: exact maxima over its 128x16 tiles
+            // tile grid of the resize kernel (k_pyr_resize: rs_tile_span) and the exact maxima of its shared-memory source window
+            pe->rs_split_x[l] = rs_axis_split(V.w, ORBX_RS_TW, 4);
+            pe->rs_split_y[l] = rs_axis_split(V.h, ORBX_RS_TH, 1);
             int rows = 1, cols = 1;
-            for (int y0 = 0; y0 < V.h; y0 += ORBX_RS_TH) {
-                const int yl = std::min(y0 + ORBX_RS_TH, V.h) - 1;
-                rows = std::max(rows, std::min(pe->ytab[V.ytab_off + yl].x + 1, S.h - 1) - pe->ytab[V.ytab_off + y0].x + 1);
-            }
-            for (int x0 = 0; x0 < V.w; x0 += ORBX_RS_TW) {
-                const int xl = std::min(x0 + ORBX_RS_TW, V.w) - 1;
-                cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
+            for (int pass = 0; pass < 2; ++pass) {          // pass 0: plain grid (latency instance, subsets of 64-row tiles), pass 1: split grid
+                const int sx = pass ? pe->rs_split_x[l] : 0, sy = pass ? pe->rs_split_y[l] : 0;
+                const int nby = (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nbx = (V.w + ORBX_RS_TW - 1) / ORBX_RS_TW;
+                for (int b = 0; b < nby; ++b) {
+                    int o, n;
+                    rs_host_span(b, nby, ORBX_RS_TH, V.h, sy, o, n);
+                    rows = std::max(rows, std::min(pe->ytab[V.ytab_off + o + n - 1].x + 1, S.h - 1) - pe->ytab[V.ytab_off + o].x + 1);
+                }
+                for (int b = 0; b < nbx; ++b) {
+                    int o, n;
+                    rs_host_span(b, nbx, ORBX_RS_TW, V.w, sx, o, n);
+                    cols = std::max(cols, std::min(pe->xtab[V.xtab_off + o + n - 1].x + 1, S.w - 1) - pe->xtab[V.xtab_off + o].x + 1);
+                }
             }
             pe->rs_rows[l] = rows;
             pe->rs_pitch[l] = (int)align_up(cols + 15 + 15, 16);     // 16-byte aligned window start + whole 16-byte vectors
@@ -278,11 +309,13 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
         if (V.nCols < 1 || V.nRows < 1) { delete pe; return fail(h, ORBX_ERR_LEVEL_TOO_SMALL, "pyramid level narrower than one FAST cell (division by zero in the reference, ORBextractor.cc:794)"); }
         V.wCell = (int)ceilf(fwidth / V.nCols); V.hCell = (int)ceilf(fheight / V.nRows);
         V.cell_off = (int)pe->cells.size();
+        V.tile_off = (int)pe->tiles.size();
         for (int i = 0; i < V.nRows; ++i) {
             const float iniY = (float)(minBY + i * V.hCell);
             float maxY = iniY + V.hCell + 6;
             if (iniY >= maxBY - 3) continue;
             if (maxY > maxBY) maxY = (float)maxBY;
+            const size_t row_first = pe->cells.size();
             for (int j = 0; j < V.nCols; ++j) {
                 const float iniX = (float)(minBX + j * V.wCell);
                 float maxX = iniX + V.wCell + 6;
@@ -313,8 +346,47 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 pe->cells.push_back(c);
                 maxcw = std::max(maxcw, cw); maxch = std::max(maxch, ch);
             }
+            // k_fast_tiles: the row's cells (consecutive columns from 0: cells are only ever skipped at the right end) in
+            // runs of at most ORBX_FT_MAXC, balanced
+            const int nv = (int)(pe->cells.size() - row_first);
+            const int ntr = (nv + ORBX_FT_MAXC - 1) / ORBX_FT_MAXC;
+            for (int t = 0, j0 = 0; t < ntr; ++t) {
+                const int nc = nv / ntr + (t < nv % ntr ? 1 : 0);
+                const OrbxCell& a = pe->cells[row_first + j0];
+                const OrbxCell& z = pe->cells[row_first + j0 + nc - 1];
+                OrbxFastTile T;
+                memset(&T, 0, sizeof(T));
+                T.x0 = a.x0; T.y0 = a.y0; T.tw = (uint16_t)(z.x0 + z.cw - a.x0); T.th = a.ch;
+                T.level = (uint8_t)l; T.ncells = (uint8_t)nc; T.wcell = (uint16_t)V.wCell;
+                T.ordbase = a.ordbase; T.xoff = a.xoff; T.yoff = a.yoff;
+                T.cmagic = 0xffffffffu / (unsigned)V.wCell + 1u;
+                const int a16 = (ORBX_PADL + T.x0) & 15;
+                const int lo = a16 + 3, hi = a16 + T.tw - 4;                  // first / last interior byte of a tile row
+                const int pq0 = lo >> 3, pq1 = hi >> 3, npairs = pq1 - pq0 + 1;
+                T.pq0 = (uint8_t)pq0; T.npairs = (uint8_t)npairs;
+                T.pmagic = 0xffffffffu / (unsigned)npairs + 1u;
+                T.nitems = (uint16_t)(npairs * (T.th - 6));
+                auto spread8 = [](unsigned m) {
+                    return (m & 1u) | ((m & 2u) << 15) | ((m & 4u) >> 1) | ((m & 8u) << 14) | ((m & 0x10u) >> 2) | ((m & 0x20u) << 13) |
+                           ((m & 0x40u) >> 3) | ((m & 0x80u) << 12);
+                };
+                T.first_mask = spread8((0xffu << (lo - 8 * pq0)) & 0xffu);
+                T.last_mask = spread8(0xffu >> (8 * pq1 + 7 - hi));
+                for (int c = 0; c < nc; ++c) {                                // the layout k_fast_tiles relies on
+                    const OrbxCell& q = pe->cells[row_first + j0 + c];
+                    if (q.x0 != a.x0 + c * V.wCell || q.y0 != a.y0 || q.ch != a.ch || (c < nc - 1 && q.cw != V.wCell + 6) || q.cw > V.wCell + 6) {
+                        delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "internal: irregular FAST cell row");
+                    }
+                }
+                if (npairs > 255 || npairs * (T.th - 6) > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
+                pe->tiles.push_back(T);
+                ft_maxtw = std::max(ft_maxtw, (int)T.tw); ft_maxth = std::max(ft_maxth, (int)T.th);
+                ft_qcap = std::max(ft_qcap, (T.tw - 6) * (T.th - 6));
+                j0 += nc;
+            }
         }
         V.ncells = (int)pe->cells.size() - V.cell_off;
+        V.ntiles = (int)pe->tiles.size() - V.tile_off;
         // quadtree, :548-550
         V.N = h->quota[l];
         V.nIni = (int)roundf((float)(maxBX - minBX) / (maxBY - minBY));
@@ -342,6 +414,17 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.fast_tp = (int)align_up(maxcw + 6, 4);
     P.fast_trows = maxch;
     P.fast_qcap = (int)align_up((long long)(maxcw - 6) * (maxch - 6), 2);
+    P.ntiles_total = (int)pe->tiles.size();
+    P.ft_tp = (int)align_up(15 + ft_maxtw + 12, 16);       // alignment slack + the word right of the last pair
+    P.ft_trows = ft_maxth;
+    P.ft_qcap = (int)align_up(ft_qcap, 8);
+    pe->ft_smem = 2 * (size_t)P.ft_tp * P.ft_trows + 2 * (size_t)P.ft_qcap;
+    if (pe->ft_smem > 200 * 1024 || (long long)P.ft_tp * P.ft_trows > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
+    {   // p / ft_tp by __umulhi in k_fast_tiles: exact over the tile's byte range
+        const unsigned m = 0xffffffffu / (unsigned)P.ft_tp + 1u;
+        for (unsigned pp = 0; pp < (unsigned)(P.ft_tp * P.ft_trows); ++pp)
+            if ((unsigned)(((unsigned long long)pp * m) >> 32) != pp / (unsigned)P.ft_tp) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "internal: tile pitch magic"); }
+    }
     pe->pyr_stride = align_up(plane_off, 256);
     pe->blur_stride = align_up(blur_off, 256);
     pe->cand_stride = align_up(cand_off, 4);
@@ -365,6 +448,8 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     if (!pe->xtab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_xtab, pe->xtab.data(), pe->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->ytab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_ytab, pe->ytab.data(), pe->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->cells.empty()) ORBX_CUDA(cudaMemcpy(pe->d_cells, pe->cells.data(), pe->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
+    ORBX_CUDA(cudaMalloc(&pe->d_tiles, std::max<size_t>(pe->tiles.size(), 1) * sizeof(OrbxFastTile)));
+    if (!pe->tiles.empty()) ORBX_CUDA(cudaMemcpy(pe->d_tiles, pe->tiles.data(), pe->tiles.size() * sizeof(OrbxFastTile), cudaMemcpyHostToDevice));
     *out = pe;
     return ORBX_OK;
 }
@@ -402,7 +487,7 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
     }
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
-    w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells;
+    w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.tiles = pe->d_tiles;
     w.pattern_f = h->d_pattern_f; w.angle_w = h->d_angle_w; w.blur_tiles = pe->d_blur_tiles;
     return ORBX_OK;
 }
@@ -473,6 +558,11 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         ORBX_CUDA(cudaEventRecord(se->ev[0], st));
     }
     int64_t launches = 0;
+    // NVTX ranges around the launches of each stage (the reference's only tracing is a std::chrono pair
+    // around ExtractORB, src/Frame.cc:106-117); they show up on the host timeline of nsys / ncu and cost nothing otherwise.
+    nvtxRangePushA("orbx:pyramid");
+    struct NvtxPop { ~NvtxPop() { nvtxRangePop(); } } nvtx_pop;
+    auto nvtx_stage = [](const char* name) { nvtxRangePop(); nvtxRangePushA(name); };
     // Single-frame graphs (one or two frames, everything captured): FAST and the quadtree of level l form their own branch
     // that starts as soon as level l exists, instead of waiting for the whole pyramid -- level 0's quadtree is the longest
     // kernel of a frame and now runs beside the resize cascade.
@@ -485,8 +575,11 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         cudaStream_t sl = h->s_lvl[l];
         ORBX_CUDA(cudaEventRecord(h->ev_lvl_ready[l], st));
         ORBX_CUDA(cudaStreamWaitEvent(sl, h->ev_lvl_ready[l], 0));
-        k_fast_cells<<<dim3((V.ncells + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, sl>>>(P, ws, V.cell_off,
-                                                                                                                          V.cell_off + V.ncells);
+        if (h->fast_v1)
+            k_fast_cells<<<dim3((V.ncells + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, sl>>>(P, ws, V.cell_off,
+                                                                                                                              V.cell_off + V.ncells);
+        else if (V.ntiles > 0)
+            k_fast_tiles<<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         k_octree<ORBX_QT_THREADS_BIG><<<dim3(1, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
         launches += 2;
         ORBX_CUDA(cudaEventRecord(h->ev_lvl_done[l], sl));
@@ -496,7 +589,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         {
             const OrbxLevel& V = P.lv[0];
             const dim3 blk(32, 8);
-            const dim3 grd(((V.w + 15) / 16 + 31) / 32, (V.h + 7) / 8, nf);
+            const dim3 grd((V.pitch / 16 + 31) / 32, (V.plane_rows + 7) / 8, nf);     // whole plane: level 0 and its border in one pass
             const int aligned16 = ((uintptr_t)d_imgs % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0) ? 1 : 0;
             k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride, aligned16);
             ++launches;
@@ -512,13 +605,14 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             const int pitch = fixed ? ORBX_RS_PITCH : pe->rs_pitch[l];
             const size_t smem = rs_smem_bytes(pe->rs_rows[l], pitch);
             if (lat) {
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
+                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
             } else {
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                const int sx = pe->rs_split_x[l], sy = pe->rs_split_y[l];
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
+                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
             }
             ++launches;
             if (per_level) { const int rb = level_branch(l); if (rb != ORBX_OK) return rb; }
@@ -532,10 +626,12 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             ORBX_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
             sb = h->s_side;
         }
-        {
+        if (nf <= 2 && P.nlevels > 1) {
+            // latency instance (16-row resize tiles): borders of levels >= 1 by their own kernel, on the side branch.  The
+            // throughput instance writes them from the resize tiles that produce the edge pixels; level 0 always has its own.
             int max_rows = 0;
-            for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
-            k_pyr_border<<<dim3((max_rows + ORBX_BORDER_ROWS - 1) / ORBX_BORDER_ROWS, P.nlevels, nf), dim3(16, 16), 0, sb>>>(P, ws);
+            for (int l = 1; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
+            k_pyr_border<<<dim3((max_rows + ORBX_BORDER_ROWS - 1) / ORBX_BORDER_ROWS, P.nlevels - 1, nf), dim3(16, 16), 0, sb>>>(P, ws);
             ++launches;
         }
         if (fork) {
@@ -546,6 +642,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
     }
     const bool forked = in_capture && stages == STAGES_ALL;
     if (se) ORBX_CUDA(cudaEventRecord(se->ev[1], st));
+    nvtx_stage("orbx:fast");
     if (per_level) {
         for (int l = 0; l < P.nlevels; ++l) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_lvl_done[l], 0));
         ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -554,9 +651,13 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         ++launches;
     } else if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
-        k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, 0, P.ncells_total);
+        if (h->fast_v1)
+            k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, 0, P.ncells_total);
+        else if (P.ntiles_total > 0)
+            k_fast_tiles<<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
+        nvtx_stage("orbx:octree");
         // levels of a megapixel or more hold tens of thousands of candidates each: their quadtrees get 1024-thread CTAs
         const int nbig = qt_big_levels(P);
         if (nbig > 0) {
@@ -570,6 +671,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             ++launches;
         }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
+        nvtx_stage("orbx:blur");
         if (forked) {
             ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         } else {
@@ -577,6 +679,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             ++launches;
         }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
+        nvtx_stage("orbx:describe");
         k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
             P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         ++launches;
@@ -676,6 +779,7 @@ int set_kernel_attrs_device(OrbxHandle* h) {
     int optin = 0;
     ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     ORBX_CUDA(raise_smem_limit(k_fast_cells, optin));
+    ORBX_CUDA(raise_smem_limit(k_fast_tiles, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_LAT>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_BIG>, optin));
@@ -754,6 +858,7 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     if (h->prm.max_batch == 0) h->prm.max_batch = 1;
     h->cand_per_cell = prm->cand_per_cell > 0 ? prm->cand_per_cell : 64;
     h->device = device;
+    if (const char* e1 = getenv("ORBX_FAST_V1")) h->fast_v1 = atoi(e1) != 0;
     build_ctor_tables(h);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -29,23 +29,46 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // =================================================================================================
 // K1  ComputePyramid.
 // =================================================================================================
-// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213): this kernel copies the image into the level-0
-// ROI (16 bytes per thread; 128-bit loads when the source rows are 16-byte aligned), k_pyr_border then fills
-// the border of every level.
+// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213).  One thread per 16-byte chunk of a PLANE row (border
+// included): chunks inside the image are 128-bit copies (when the source rows are 16-byte aligned), the chunks that touch
+// the 19-px border gather their bytes through the reflect-101 index -- the border never needs a second pass over HBM.
 __global__ void __launch_bounds__(256)
 k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8_t* __restrict__ imgs,
              long long row_stride, long long frame_stride, int aligned16) {
     const OrbxLevel& L = plan.lv[0];
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte chunk of the plane row; level column 0 sits at byte ORBX_PADL
+    const int pr = blockIdx.y * blockDim.y + threadIdx.y;         // plane row
     const int frame = blockIdx.z;
-    if (x >= L.w || y >= L.h) return;
-    const uint8_t* srow = imgs + (long long)frame * frame_stride + (long long)y * row_stride + x;
-    uint8_t* drow = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + y) * L.pitch + ORBX_PADL + x;
-    if (aligned16 && x + 16 <= L.w) {
-        *reinterpret_cast<uint4*>(drow) = __ldg(reinterpret_cast<const uint4*>(srow));
+    const int x = 16 * chunk - ORBX_PADL;                         // level column of the chunk's first byte
+    if (pr >= L.plane_rows || x >= L.w + ORBX_EDGE || x + 16 <= -ORBX_EDGE) return;
+    const int sy = reflect101(pr - ORBX_EDGE, L.h);
+    const uint8_t* srow = imgs + (long long)frame * frame_stride + (long long)sy * row_stride;
+    uint8_t* drow = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)pr * L.pitch + 16 * chunk;
+    if (x >= 0 && x + 16 <= L.w) {
+        if (aligned16) {
+            *reinterpret_cast<uint4*>(drow) = __ldg(reinterpret_cast<const uint4*>(srow + x));
+        } else {
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                v[q] = (uint32_t)__ldg(srow + x + 4 * q) | ((uint32_t)__ldg(srow + x + 4 * q + 1) << 8) | ((uint32_t)__ldg(srow + x + 4 * q + 2) << 16) |
+                       ((uint32_t)__ldg(srow + x + 4 * q + 3) << 24);
+            *reinterpret_cast<uint4*>(drow) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
     } else {
-        for (int j = 0; j < 16 && x + j < L.w; ++j) drow[j] = __ldg(srow + j);
+        // chunk on the left / right edge: bytes outside [-19, w+19) are padding (written with a clamped index, never read)
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = min(max(x + 4 * q + j, -ORBX_EDGE), L.w + ORBX_EDGE - 1);
+                wv |= (uint32_t)__ldg(srow + reflect101(xx, L.w)) << (8 * j);
+            }
+            v[q] = wv;
+        }
+        *reinterpret_cast<uint4*>(drow) = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -90,21 +113,58 @@ __device__ __forceinline__ void rs_hpass(const uint8_t* __restrict__ q0, const u
 
 // TH: tile height.  ORBX_RS_TH for throughput; ORBX_RS_TH_LAT for one or two frames, where a level is a handful of tiles and
 // the kernel time is one CTA's latency (more, smaller CTAs finish sooner).
+// Reflect-101 border words of one plane row (copyMakeBorder, :1193).  srow / drow: the source level row and the destination
+// plane row as words, word 0 = level column 0.  A border word (4 pixels) is a byte-reversed, funnel-shifted window of the
+// level row: left-strip pixels dx..dx+3 (dx < 0) mirror level pixels -dx-3..-dx, right-strip pixels mirror 2(w-1)-dx-3..2(w-1)-dx.
+__device__ __forceinline__ void border_left_word(const uint32_t* __restrict__ srow, uint32_t* __restrict__ drow, int wx /* -5..-1 */) {
+    const int k = -wx - 1;                                     // level words k, k+1 hold pixels 4k+1 .. 4k+4
+    const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8);
+    drow[wx] = __byte_perm(v, 0, 0x0123);                      // pixel -20 (byte 0 of word -5) is padding
+}
+__device__ __forceinline__ void border_right_word(const uint32_t* __restrict__ srow, uint32_t* __restrict__ drow, int wx, int w) {
+    const int dx0 = 4 * wx;
+    const int s0 = 2 * (w - 1) - dx0 - 3;                      // first mirrored level pixel (>= 0 since w > 22)
+    const int k = s0 >> 2;
+    const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8 * (s0 & 3));
+    uint32_t word = __byte_perm(v, 0, 0x0123);
+    const int keep = w - dx0;                                  // level bytes at the start of a word straddling level / border
+    if (keep > 0) {
+        const uint32_t orig = srow[wx];
+        const uint32_t sel = keep == 1 ? 0x7650u : (keep == 2 ? 0x7610u : 0x7210u);
+        word = __byte_perm(orig, word, sel);
+    }
+    drow[wx] = word;
+}
+
+// Tile grid of k_pyr_resize along one axis: tiles of `full` pixels from the origin; when the remainder is shorter than
+// ORBX_RS_MIN_EDGE the last two tiles share what is left (`split` = extent of the second-to-last one, else 0), so that
+// the tile holding an edge always holds the >= 28 pixels the reflect-101 border of that edge mirrors.
+#define ORBX_RS_MIN_EDGE 32
+__device__ __forceinline__ void rs_tile_span(int b, int nb, int full, int len, int split, int& o, int& n) {
+    o = b * full;
+    n = min(full, len - o);
+    if (split > 0) {
+        if (b == nb - 2) n = split;
+        else if (b == nb - 1) { o = (nb - 2) * full + split; n = len - o; }
+    }
+}
+
 template <bool AREA, int PITCH, int TH>
 __global__ void __launch_bounds__(256)
-k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
+k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt, int split_x, int split_y) {
     extern __shared__ __align__(16) uint8_t smem_rs[];
     const int src_pitch_s = PITCH ? PITCH : src_pitch_rt;
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * ORBX_RS_TW, y0 = blockIdx.y * TH;
+    int x0, y0, tw, th;                                                   // this tile's origin and extent
+    rs_tile_span(blockIdx.x, gridDim.x, ORBX_RS_TW, L.w, split_x, x0, tw);
+    rs_tile_span(blockIdx.y, gridDim.y, TH, L.h, split_y, y0, th);
     const int frame = blockIdx.z;
     uint8_t* fbase = ws.pyr + (long long)frame * ws.pyr_stride;
     const uint8_t* splane = fbase + S.plane_off;
     const int2* xtab = ws.xtab + L.xtab_off;
     const int2* ytab = ws.ytab + L.ytab_off;
-    const int tw = min(ORBX_RS_TW, L.w - x0), th = min(TH, L.h - y0);   // this tile's extent
     // source window (inclusive), second taps clamped into the level (their weight is 0 when clamped)
     const int sx_lo = __ldg(&xtab[x0]).x, sx_hi = min(__ldg(&xtab[x0 + tw - 1]).x + 1, S.w - 1);
     const int sy_lo = __ldg(&ytab[y0]).x, sy_hi = min(__ldg(&ytab[y0 + th - 1]).x + 1, S.h - 1);
@@ -204,6 +264,35 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
             }
         }
     }
+    // ---- border (copyMakeBorder BORDER_REFLECT_101, :1193): the tiles on the level's edges also write the 19-px frame next to
+    // them -- side strips of their rows, and for the top / bottom tile rows the 19 band rows above / below (their own columns,
+    // plus the strips' corners).  Every source pixel lies inside this tile (split tile grid), just written by this CTA; the
+    // border bytes are read by nobody in this launch.  split_x / split_y < 0: no border here (the latency path's 16-row tiles;
+    // k_pyr_border runs afterwards instead).
+    if (split_x < 0) return;
+    const bool left = x0 == 0, right = x0 + tw == L.w, top = y0 == 0, bottom = y0 + th == L.h;
+    if (!(left || right || top || bottom)) return;
+    __syncthreads();                                                     // this CTA's level pixels are visible to all its threads
+    {
+        uint8_t* plane = fbase + L.plane_off;
+        const int n_top = top ? ORBX_EDGE : 0, n_mid = (left || right) ? th : 0, n_bot = bottom ? ORBX_EDGE : 0;
+        const int lane = tid & 15;
+        const int rw0 = L.w >> 2, nright = ((L.w + ORBX_EDGE - 1) >> 2) - rw0 + 1;   // right-strip words (the first may straddle)
+        const int cw0 = x0 >> 2, cwn = (right ? L.w >> 2 : (x0 + tw) >> 2) - cw0;    // words of this tile fully inside the level
+        for (int idx = tid >> 4; idx < n_top + n_mid + n_bot; idx += 16) {
+            int pr, sr;                                                  // destination plane row, source level row
+            bool band = true;
+            if (idx < n_top) { pr = idx; sr = ORBX_EDGE - idx; }
+            else if (idx < n_top + n_mid) { sr = y0 + idx - n_top; pr = ORBX_EDGE + sr; band = false; }
+            else { const int j = idx - n_top - n_mid; pr = ORBX_EDGE + L.h + j; sr = L.h - 2 - j; }
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + sr) * L.pitch + ORBX_PADL);
+            uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)pr * L.pitch + ORBX_PADL);
+            if (band)
+                for (int wx = lane; wx < cwn; wx += 16) drow[cw0 + wx] = srow[cw0 + wx];
+            if (left && lane < 5) border_left_word(srow, drow, lane - 5);
+            if (right && lane >= 5 && lane - 5 < nright) border_right_word(srow, drow, rw0 + lane - 5, L.w);
+        }
+    }
 }
 
 // copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  16 lanes per plane row.  A border word
@@ -214,7 +303,7 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
 #define ORBX_BORDER_ROWS 64
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
-    const int level = blockIdx.y;
+    const int level = blockIdx.y + 1;                          // level 0's border comes from k_pyr_level0
     const int frame = blockIdx.z;
     const OrbxLevel& L = plan.lv[level];
     const int lane = threadIdx.x;                              // 0..15
@@ -248,27 +337,8 @@ k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
     const int rw0 = L.w >> 2;                                  // first right-strip word (may straddle level/border)
     const int rwl = (L.w + ORBX_EDGE - 1) >> 2;                // last word holding border pixels
     const int nright = rwl - rw0 + 1;
-    if (lane < 5) {
-        // left strip: words -5..-1 (pixels -20..-1; pixel -20 is padding)
-        const int wx = lane - 5;
-        const int k = -wx - 1;                                 // level words k, k+1 hold pixels 4k+1 .. 4k+4
-        const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8);
-        drow[wx] = __byte_perm(v, 0, 0x0123);
-    } else if (lane - 5 < nright) {
-        const int wx = rw0 + (lane - 5);
-        const int dx0 = 4 * wx;
-        const int s0 = 2 * (L.w - 1) - dx0 - 3;                // first mirrored level pixel (>= 0 since w > 22)
-        const int k = s0 >> 2;
-        const uint32_t v = __funnelshift_r(srow[k], srow[k + 1], 8 * (s0 & 3));
-        uint32_t word = __byte_perm(v, 0, 0x0123);
-        const int keep = L.w - dx0;                            // level bytes at the start of a straddling word
-        if (keep > 0) {
-            const uint32_t orig = srow[wx];
-            const uint32_t sel = keep == 1 ? 0x7650u : (keep == 2 ? 0x7610u : 0x7210u);
-            word = __byte_perm(orig, word, sel);
-        }
-        drow[wx] = word;
-    }
+    if (lane < 5) border_left_word(srow, drow, lane - 5);      // left strip: words -5..-1 (pixels -20..-1; pixel -20 is padding)
+    else if (lane - 5 < nright) border_right_word(srow, drow, rw0 + (lane - 5), L.w);
     }
 }
 
@@ -494,6 +564,272 @@ k_fast_cells(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int c
             }
         }
         written += __popc(bal);
+    }
+}
+
+// =================================================================================================
+// K2 (v2)  The same cell loop, one CTA per TILE = up to ORBX_FT_MAXC consecutive cells of one cell row.
+//
+// k_fast_cells spends most of its instructions around the arithmetic: a warp per cell stages 36x36 pixels for a 30x30
+// interior with 4-byte copies and a division per word, every per-cell prologue instruction costs a full warp for 900
+// pixels, queues of ~150 entries and candidate lists of ~17 leave lanes idle, and the queue is walked three times.
+// Here a CTA of 256 threads owns one image of ~223x38 pixels (16-byte cp.async rows, no per-word index arithmetic),
+// shares one queue (full warps in every phase), and replaces the queue walks of NMS / emission by one dense pass
+// over the score map (95 % of its words are zero: one LDS + one test per 4 pixels).
+//
+// Semantics kept exactly (ORBextractor.cc:797-864): cv::FAST(iniThFAST, nonmax) per cell; a cell that yields no keypoint is
+// run again with minThFAST.  NMS never looks across a cell's detection interior (neighbours outside count as 0): the dense
+// pass masks the left / right neighbours at cell boundary columns; the rows above / below the interior are never scored.
+// "Cell yields nothing at iniThFAST" is decided after NMS (two equal adjacent maxima suppress each other), per cell, by a
+// flag word; only the empty cells are then scanned again at minThFAST.
+// =================================================================================================
+#define ORBX_FT_THREADS 256
+
+// Pair-bound flags of the 4 pixels of one aligned word: bit 15 / 31 of the two returned words = pixels (0,1) / (2,3).
+// c, u, d: the word and the same word 3 rows up / down; l, r: the word shifted by 3 pixels left / right.
+// KT = (0x8000 - (th + 1)) in both halves: bit 15 of x - y + KT is set iff x - y > th (|x - y| <= 255, no borrow crosses halves).
+__device__ __forceinline__ void ft_word_flags(unsigned c, unsigned u, unsigned d, unsigned l, unsigned r, unsigned KT, unsigned& z0, unsigned& z1) {
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const unsigned sel = hlf ? 0x4342u : 0x4140u;
+        const unsigned c2 = __byte_perm(c, 0, sel), u2 = __byte_perm(u, 0, sel), d2 = __byte_perm(d, 0, sel);
+        const unsigned l2 = __byte_perm(l, 0, sel), r2 = __byte_perm(r, 0, sel);
+        const unsigned dk = __vmaxs2(__vmins2(u2, d2), __vmins2(l2, r2));     // every arc of 9 holds one pixel of each antipodal pair
+        const unsigned br = __vmins2(__vmaxs2(u2, d2), __vmaxs2(l2, r2));
+        const unsigned z = (c2 - dk + KT) | (br - c2 + KT);
+        if (hlf) z1 = z; else z0 = z;
+    }
+}
+
+// Flags of one aligned 8-byte pair (8 pixels) at 32-bit word index b of the tile, in the layout
+// {bit 0, 16, 1, 17, 2, 18, 3, 19} = pixels 0..7 (other bits are garbage: the caller masks with its valid-pixel word).
+__device__ __forceinline__ unsigned ft_pair_flags(const uint32_t* __restrict__ t32, int b, int tpw, unsigned KT) {
+    const unsigned wl = t32[b - 1], wr = t32[b + 2];
+    const uint2 wc = *reinterpret_cast<const uint2*>(t32 + b);
+    const uint2 wu = *reinterpret_cast<const uint2*>(t32 + b - 3 * tpw);
+    const uint2 wd = *reinterpret_cast<const uint2*>(t32 + b + 3 * tpw);
+    unsigned z00, z01, z10, z11;
+    ft_word_flags(wc.x, wu.x, wd.x, __funnelshift_r(wl, wc.x, 8), __funnelshift_r(wc.x, wc.y, 24), KT, z00, z01);
+    ft_word_flags(wc.y, wu.y, wd.y, __funnelshift_r(wc.x, wc.y, 8), __funnelshift_r(wc.y, wr, 24), KT, z10, z11);
+    return (z00 >> 15) | (z01 >> 14) | (z10 >> 13) | (z11 >> 12);
+}
+
+// 8-bit pixel mask of a pair -> the flag layout above
+__device__ __forceinline__ unsigned ft_spread8(unsigned m) {
+    return (m & 1u) | ((m & 2u) << 15) | ((m & 4u) >> 1) | ((m & 8u) << 14) | ((m & 0x10u) >> 2) | ((m & 0x20u) << 13) | ((m & 0x40u) >> 3) |
+           ((m & 0x80u) << 12);
+}
+
+// Queue the flagged pixels of one pair; p0 = tile byte index of the pair's first pixel.
+__device__ __forceinline__ int ft_queue_pair(uint16_t* __restrict__ queue, int pos, unsigned mk, int p0) {
+    if (mk & 0x00000001u) queue[pos++] = (uint16_t)(p0 + 0);
+    if (mk & 0x00010000u) queue[pos++] = (uint16_t)(p0 + 1);
+    if (mk & 0x00000002u) queue[pos++] = (uint16_t)(p0 + 2);
+    if (mk & 0x00020000u) queue[pos++] = (uint16_t)(p0 + 3);
+    if (mk & 0x00000004u) queue[pos++] = (uint16_t)(p0 + 4);
+    if (mk & 0x00040000u) queue[pos++] = (uint16_t)(p0 + 5);
+    if (mk & 0x00000008u) queue[pos++] = (uint16_t)(p0 + 6);
+    if (mk & 0x00080000u) queue[pos++] = (uint16_t)(p0 + 7);
+    return pos;
+}
+
+__global__ void __launch_bounds__(ORBX_FT_THREADS)
+k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int tile_base) {
+    extern __shared__ __align__(16) uint8_t smem_ft[];
+    __shared__ int s_qn, s_ns, s_flags, s_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int frame = blockIdx.y;
+    OrbxFastTile T;
+    {
+        const uint4* tp4 = reinterpret_cast<const uint4*>(ws.tiles + tile_base + blockIdx.x);
+        uint4* d = reinterpret_cast<uint4*>(&T);
+        d[0] = __ldg(tp4); d[1] = __ldg(tp4 + 1); d[2] = __ldg(tp4 + 2);
+    }
+    const OrbxLevel& L = plan.lv[T.level];
+    const int tp = plan.ft_tp, tpw = tp >> 2;
+    const int map_bytes = tp * plan.ft_trows;                       // multiple of 16
+    uint8_t* tile = smem_ft;
+    uint8_t* score = smem_ft + map_bytes;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(smem_ft + 2 * map_bytes);
+    const int th_rows = T.th, tw = T.tw;
+    const int a16 = (ORBX_PADL + T.x0) & 15;
+
+    // ---- stage the tile image: whole 16-byte chunks of the plane rows (64-byte aligned), score map cleared meanwhile ----
+    {
+        const uint8_t* g = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + T.y0) * L.pitch + (ORBX_PADL + T.x0 - a16);
+        const int nvec = (a16 + tw + 15) >> 4;
+        const unsigned vmagic = 65536u / (unsigned)nvec + 1u;          // i / nvec for i < 2^11 (nvec <= 32)
+        const int total = nvec * th_rows;
+        for (int i = tid; i < total; i += ORBX_FT_THREADS) {
+            const int r = (int)(((unsigned)i * vmagic) >> 16);
+            const int v = i - r * nvec;
+            __pipeline_memcpy_async(tile + r * tp + 16 * v, g + (long long)r * L.pitch + 16 * v, 16);
+        }
+        __pipeline_commit();
+        const int nz = (th_rows * tp) >> 4;
+        for (int i = tid; i < nz; i += ORBX_FT_THREADS) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { s_qn = 0; s_ns = 0; s_flags = 0; }
+        __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+    const int nrows = th_rows - 6;
+    const int ncells = T.ncells, wcell = T.wcell;
+    const unsigned all_cells = (1u << ncells) - 1u;
+    int* counter = ws.cand_count + frame * plan.nlevels + T.level;
+    uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
+    const unsigned tpmagic = 0xffffffffu / (unsigned)tp + 1u;          // p / tp by __umulhi (p < 2^16; checked by the host for the plan's tp)
+
+    unsigned empty = all_cells;                                        // cells still without a keypoint
+    for (int phase = 0; phase < 2; ++phase) {
+        int use_th = plan.ini_th;
+        if (phase == 1) {
+            if (plan.min_th >= plan.ini_th || empty == 0u) break;      // a lower threshold cannot add to a cell that has keypoints
+            use_th = plan.min_th;
+        }
+        const unsigned KT = (0x8000u - (unsigned)(use_th + 1)) * 0x00010001u;
+        // ---- stage 1: pair bound on aligned 8-pixel pairs, survivors queued (two pairs per thread and scan) ----
+        if (phase == 0) {
+            const int nitems = T.nitems, npairs = T.npairs, pq0 = T.pq0;
+            for (int base = 0; base < nitems; base += 2 * ORBX_FT_THREADS) {
+                unsigned mk[2] = {0u, 0u};
+                int p0[2] = {0, 0};
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int i = base + g * ORBX_FT_THREADS + tid;
+                    if (i < nitems) {
+                        const int r = (int)__umulhi((unsigned)i, T.pmagic);
+                        const int k = i - r * npairs;
+                        const int b = (r + 3) * tpw + 2 * (pq0 + k);
+                        const unsigned valid = (k == 0 ? T.first_mask : 0x000f000fu) & (k == npairs - 1 ? T.last_mask : 0x000f000fu);
+                        mk[g] = ft_pair_flags(t32, b, tpw, KT) & valid;
+                        p0[g] = 4 * b;
+                    }
+                }
+                const int cnt = __popc(mk[0]) + __popc(mk[1]);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t_ = __shfl_up_sync(ORBX_FULL_MASK, inc, o);
+                    if (lane >= o) inc += t_;
+                }
+                int wbase = 0;
+                if (lane == 31 && inc > 0) wbase = atomicAdd(&s_qn, inc);
+                wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 31);
+                int pos = wbase + inc - cnt;
+                pos = ft_queue_pair(queue, pos, mk[0], p0[0]);
+                ft_queue_pair(queue, pos, mk[1], p0[1]);
+            }
+        } else {
+            // only the cells that came out empty: items = (empty cell, row, pair of the cell's column span)
+            const int ne = __popc(empty);
+            const int ppc = (wcell >> 3) + 2;                          // a span of wcell bytes touches at most this many 8-byte pairs
+            const unsigned per_cell = (unsigned)(nrows * ppc);
+            const unsigned m_cell = 0xffffffffu / per_cell + 1u, m_ppc = 0xffffffffu / (unsigned)ppc + 1u;   // exact for i < 2^15
+            const int nitems = ne * (int)per_cell;
+            const int hi_all = a16 + tw - 4;
+            for (int base = 0; base < nitems; base += ORBX_FT_THREADS) {
+                const int i = base + tid;
+                unsigned mk = 0u;
+                int p0 = 0;
+                if (i < nitems) {
+                    const int e = (int)__umulhi((unsigned)i, m_cell);
+                    const int rem = i - e * (int)per_cell;
+                    const int r = (int)__umulhi((unsigned)rem, m_ppc);
+                    const int k = rem - r * ppc;
+                    const int c = (int)__fns(empty, 0, e + 1);          // e-th empty cell
+                    const int lo = a16 + 3 + c * wcell, hi = min(lo + wcell - 1, hi_all);
+                    const int pq = (lo >> 3) + k;
+                    if (8 * pq <= hi) {
+                        const unsigned m8 = (0xffu << max(lo - 8 * pq, 0)) & (0xffu >> max(8 * pq + 7 - hi, 0)) & 0xffu;
+                        const int b = (r + 3) * tpw + 2 * pq;
+                        mk = ft_pair_flags(t32, b, tpw, KT) & ft_spread8(m8);
+                        p0 = 4 * b;
+                    }
+                }
+                const int cnt = __popc(mk);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t_ = __shfl_up_sync(ORBX_FULL_MASK, inc, o);
+                    if (lane >= o) inc += t_;
+                }
+                int wbase = 0;
+                if (lane == 31 && inc > 0) wbase = atomicAdd(&s_qn, inc);
+                wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 31);
+                ft_queue_pair(queue, wbase + inc - cnt, mk, p0);
+            }
+        }
+        __syncthreads();
+        // ---- stage 2: exact corner measure of the queued pixels ----
+        const int qn = s_qn;
+        for (int e = tid; e < qn; e += ORBX_FT_THREADS) {
+            const int p = queue[e];
+            const int best = fast_best(tile, p, tp);
+            if (best > use_th) score[p] = (uint8_t)best;
+        }
+        __syncthreads();
+        // ---- dense strict 3x3 NMS over the score map; survivors listed in the (now free) queue ----
+        {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(score);
+            const int w0 = (a16 + 3) >> 2, nw = ((a16 + tw - 4) >> 2) - w0 + 1;
+            const unsigned wmagic = 0xffffffffu / (unsigned)nw + 1u;
+            const int nitems = nw * nrows;
+            for (int i = tid; i < nitems; i += ORBX_FT_THREADS) {
+                const int r = (int)__umulhi((unsigned)i, wmagic);
+                const int w = w0 + (i - r * nw);
+                const int wi = (r + 3) * tpw + w;
+                unsigned wc = s32[wi];
+                if (wc == 0u) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int s = (int)((wc >> (8 * k)) & 0xffu);
+                    if (s == 0) continue;
+                    const int p = 4 * wi + k;
+                    const int xi = 4 * w + k - a16 - 3;                      // interior column (>= 0: only interior pixels are scored)
+                    const int c = (int)__umulhi((unsigned)xi, T.cmagic);
+                    if (!((empty >> c) & 1u)) continue;                      // phase 1: cells that already have keypoints are done
+                    const int rem = xi - c * wcell;
+                    int nb = max((int)score[p - tp], (int)score[p + tp]);
+                    if (rem != 0) nb = max(nb, max((int)score[p - 1], max((int)score[p - tp - 1], (int)score[p + tp - 1])));
+                    if (rem != wcell - 1) nb = max(nb, max((int)score[p + 1], max((int)score[p - tp + 1], (int)score[p + tp + 1])));
+                    if (s > nb) {
+                        queue[atomicAdd(&s_ns, 1)] = (uint16_t)p;
+                        atomicOr(&s_flags, 1 << c);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- emission: one atomic per tile reserves the slots; entries carry the emission-order key (:855-860) ----
+        const int ns = s_ns;
+        if (tid == 0) {
+            int b0 = 0;
+            if (ns > 0) {
+                b0 = atomicAdd(counter, ns);
+                if (b0 + ns > L.cand_cap) atomicOr(ws.flags, 1);
+            }
+            s_base = b0;
+        }
+        __syncthreads();
+        const int slot0 = s_base;
+        for (int e = tid; e < ns; e += ORBX_FT_THREADS) {
+            const int slot = slot0 + e;
+            if (slot >= L.cand_cap) break;
+            const int p = queue[e];
+            const int r = (int)__umulhi((unsigned)p, tpmagic);
+            const int x = p - r * tp - a16;                                  // tile image column (>= 3)
+            const int c = (int)__umulhi((unsigned)(x - 3), T.cmagic);
+            const int xc = x - c * wcell;                                    // column inside the cell image
+            const uint32_t resp = (uint32_t)score[p] - 1u;
+            cand[slot] = make_uint2((uint32_t)(x + T.xoff) | ((uint32_t)(r + T.yoff) << ORBX_COORD_BITS) | (resp << 24),
+                                    (T.ordbase + ((uint32_t)c << ORBX_ORD_CELL_SHIFT)) | ((uint32_t)r << 7) | (uint32_t)xc);
+        }
+        empty = all_cells & ~(unsigned)s_flags;
+        __syncthreads();                                                     // s_flags / queue are rewritten by the next phase
+        if (tid == 0) { s_qn = 0; s_ns = 0; }
+        __syncthreads();
     }
 }
 

@@ -30,6 +30,7 @@ struct OrbxLevel {
     // FAST cell grid, reference :781-814
     int nCols, nRows, wCell, hCell;
     int cell_off, ncells;  // slice of the cell table
+    int tile_off, ntiles;  // slice of the FAST tile table (k_fast_tiles)
     // quadtree, reference :548-568
     int N;                 // mnFeaturesPerLevel[level]
     int nIni;
@@ -53,6 +54,10 @@ struct OrbxPlan {
     int fast_tp;           // FAST smem tile pitch (bytes)
     int fast_trows;        // FAST smem tile rows
     int fast_qcap;         // FAST smem queue capacity (entries)
+    int ntiles_total;      // FAST tiles of all levels (k_fast_tiles)
+    int ft_tp;             // k_fast_tiles: smem tile pitch (bytes, multiple of 16), rows, queue capacity (entries)
+    int ft_trows;
+    int ft_qcap;
     int lap0, lap1;
     int umax[ORBX_HALF_PATCH + 1];
     OrbxLevel lv[ORBX_MAX_LEVELS];
@@ -74,6 +79,27 @@ struct OrbxCell {          // 32 bytes, read as two uint4
 };
 
 static_assert(sizeof(OrbxCell) == 32, "OrbxCell is read as two uint4");
+
+// One FAST tile of k_fast_tiles: `ncells` consecutive cells of one cell row (reference ORBextractor.cc:797-814), processed by
+// one CTA as a single image [x0, x0+tw) x [y0, y0+th) in level coordinates.  The cells' detection interiors tile the columns
+// [3, tw-3) without gaps: cell c owns interior columns [c*wcell, (c+1)*wcell) (the last cell of a row may be narrower).
+// In shared memory pixel (r, x) sits at byte r*ft_tp + a16 + x, a16 = (ORBX_PADL + x0) & 15.
+#define ORBX_FT_MAXC 7          // cells per tile (7 x 31 px: at most 29 aligned 8-byte pairs per row -> <= 1024 work items)
+struct OrbxFastTile {           // 48 bytes, read as three uint4
+    uint16_t x0, y0;
+    uint16_t tw, th;
+    uint8_t level, ncells;
+    uint16_t wcell;
+    uint32_t ordbase;           // (cell row * nCols + first cell column) << ORBX_ORD_CELL_SHIFT
+    uint16_t xoff, yoff;        // first cell column * wCell, cell row * hCell
+    uint32_t cmagic;            // 2^32 / wcell + 1: interior column -> cell (__umulhi)
+    uint32_t pmagic;            // 2^32 / npairs + 1: work item -> row (__umulhi)
+    uint8_t pq0, npairs;        // first 8-byte pair holding an interior pixel, pairs per row
+    uint16_t nitems;            // npairs * (th - 6)
+    uint32_t first_mask, last_mask;   // interior-pixel flags of the first / last pair, in the flag layout of k_fast_tiles
+    uint32_t reserved[2];
+};
+static_assert(sizeof(OrbxFastTile) == 48, "OrbxFastTile is read as three uint4");
 
 // Kept keypoint record written by the quadtree kernel, completed by the describe kernel.
 struct OrbxKpRec {
@@ -97,6 +123,7 @@ struct OrbxWs {
     const int2* xtab;      // resize: {src offset, a0 | a1<<16}
     const int2* ytab;
     const OrbxCell* cells;
+    const OrbxFastTile* tiles;
     const float* pattern_f;   // rBRIEF tests as floats, layout [bit k][descriptor byte][x0, y0, x1, y1]
     const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
     const uint32_t* blur_tiles; // blur tile table: level | tile_x << 8 | tile_y << 20

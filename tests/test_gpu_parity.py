@@ -364,3 +364,53 @@ def test_api_contract_errors_and_reuse(gpu, oracle, images):
     assert L.orbx_get_pyramid_level(ext._h, 1, 0, buf.ctypes.data, 10, 0) == -8      # frame 1 is not resident
     assert L.orbx_get_pyramid_level(ext._h, 0, 99, buf.ctypes.data, 10, 0) == -2     # bad level
     ext.close()
+
+
+@pytest.mark.parametrize("max_batch,counts", [(33, (34, 40, 49, 65, 67)), (64, (65, 80, 97, 111, 112, 129)), (256, (257, 270, 481, 495, 496))])
+def test_host_batch_group_ramp(gpu, max_batch, counts):
+    """Host-buffer calls ramp their launch-group size up at the start and down at the end (orbx_extract_batch).  A group must
+    never hold more frames than the workspace (= max_batch): n_frames just above max_batch, and just above the ramp sums
+    (32 + 64 + ..), once produced groups of up to max_batch + 15 frames.  Results must equal plain groups of 16."""
+    rng = np.random.default_rng(max_batch)
+    base = synth_batch(8, 128, 96, seed0=900 + max_batch)
+    n_max = max(counts)
+    frames = np.stack([np.roll(base[i % 8], (int(rng.integers(0, 96)), int(rng.integers(0, 128))), (0, 1)) for i in range(n_max)])
+    ref_ext = gpu.ORBextractor(300, 1.2, 2, 20, 7, max_batch=16)
+    rc, rk, rd = ref_ext.extract_batch_host(frames, (0, 0))
+    ref_ext.close()
+    ext = gpu.ORBextractor(300, 1.2, 2, 20, 7, max_batch=max_batch)
+    for n in counts:
+        c, k, d = ext.extract_batch_host(frames[:n], (0, 0))
+        assert np.array_equal(c, rc[:n]), n
+        for f in range(n):
+            m = c[f, 0]
+            assert k[f, :m].tobytes() == rk[f, :m].tobytes() and np.array_equal(d[f, :m], rd[f, :m]), (n, f)
+    ext.close()
+
+
+def test_fast_v1_v2_same_candidates(gpu, monkeypatch):
+    """The tile kernel (k_fast_tiles) against the round-1 warp-per-cell kernel (ORBX_FAST_V1=1) on geometries that stress the
+    tile layout: odd widths (every 16-byte alignment of the first tile column), cell sizes 25..60, low contrast (many cells
+    re-run at minThFAST), noise (full queues)."""
+    rng = np.random.default_rng(5)
+    cases = [(640, 480, 30, "synth"), (641, 479, 30, "synth"), (333, 217, 30, "low"), (517, 389, 35, "synth"), (400, 300, 25, "noise"),
+             (752, 480, 60, "synth"), (203, 167, 30, "low"), (1241, 376, 30, "synth"), (319, 241, 47, "noise")]
+    for w, h, cell, kind in cases:
+        if kind == "noise":
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        else:
+            img = synth_frame(w + h, w, h)
+            if kind == "low":
+                img = (img // 10 + 90).astype(np.uint8)
+        out = []
+        for v1 in ("1", "0"):
+            monkeypatch.setenv("ORBX_FAST_V1", v1)
+            e = gpu.ORBextractor(1500, 1.2, 4, 20, 7, cell_size=cell)
+            ret, kps, desc = e(img, None, (0, 0))
+            out.append(([e.level_candidates(l) for l in range(4)], kps, desc))
+            e.close()
+        monkeypatch.delenv("ORBX_FAST_V1")
+        for l in range(4):
+            for a, b in zip(out[0][0][l], out[1][0][l]):
+                assert np.array_equal(a, b), (w, h, cell, kind, l)
+        assert kp_bytes_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
