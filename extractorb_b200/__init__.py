@@ -14,12 +14,13 @@ import os
 import numpy as np
 
 __all__ = ["ORBextractor", "OrbxError", "OrbxParams", "KP_DTYPE", "load_library", "library_path", "STAGE_NAMES", "stereo_match",
-           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe", "extract_frame"]
+           "FrameCalib", "image_bounds", "undistort_grid", "search_for_initialization", "FRAME_GRID_COLS", "FRAME_GRID_ROWS", "clahe", "extract_frame", "extract_batch_multi",
+           "extract_batch_multi_raw"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_NAMES = ("pyramid", "fast", "octree", "blur", "describe")
 MEM_HOST, MEM_DEVICE = 0, 1
-FLAG_PROFILE = 1
+FLAG_PROFILE, FLAG_NO_GRAPH, FLAG_SINGLE_STREAM, FLAG_COPY_ONLY = 1, 2, 4, 8
 
 # cv::KeyPoint layout (28 bytes)
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -76,6 +77,7 @@ def load_library():
     L.orbx_max_keypoints.argtypes = [vp, i32, i32]
     L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, i32, i32, vp, vp, i32, vp, i32, vp]
+    L.orbx_extract_batch_multi.argtypes = [C.POINTER(vp), i32, vp, i32, i32, i32, sz, sz, i32, i32, vp, vp, i32, vp, vp]
     L.orbx_compute_pyramid.argtypes = [vp, vp, i32, i32, sz]
     L.orbx_compute_keypoints_octtree.argtypes = [vp]
     L.orbx_distribute_octtree.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32)]
@@ -113,11 +115,11 @@ class ORBextractor:
     HARRIS_SCORE, FAST_SCORE = 0, 1
 
     def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, *, device=0, max_batch=1,
-                 cell_size=30, cand_per_cell=0, profile=False):
+                 cell_size=30, cand_per_cell=0, profile=False, flags=0):
         self._L = load_library()
         self._h = C.c_void_p()
         prm = OrbxParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, cell_size, max_batch, cand_per_cell,
-                         FLAG_PROFILE if profile else 0)
+                         (FLAG_PROFILE if profile else 0) | flags)
         rc = self._L.orbx_create(C.byref(prm), device, C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -283,6 +285,32 @@ class ORBextractor:
     @property
     def stream(self):
         return self._L.orbx_get_stream(self._h)
+
+
+def extract_batch_multi_raw(extractors, images_ptr, n_frames, width, height, row_stride, frame_stride, lap, kps_ptr, desc_ptr,
+                            cap_per_frame, counts_ptr):
+    """orbx_extract_batch_multi: one process, one host thread + handle per device, launch groups pulled from a shared cursor.
+    `extractors`: ORBextractor instances (one per device); all pointers are HOST memory.  -> frames processed per extractor."""
+    n = len(extractors)
+    hs = (C.c_void_p * n)(*[e._h for e in extractors])
+    per = (C.c_int32 * n)()
+    e0 = extractors[0]
+    e0._check(e0._L.orbx_extract_batch_multi(hs, n, images_ptr, n_frames, width, height, row_stride, frame_stride, int(lap[0]), int(lap[1]),
+                                             kps_ptr, desc_ptr, cap_per_frame, counts_ptr, C.cast(per, C.c_void_p)))
+    return list(per)
+
+
+def extract_batch_multi(extractors, frames, vLappingArea=(0, 0)):
+    """frames: (F,H,W) uint8 host array sharded over `extractors` -> (counts[F,2], kps[F,cap], desc[F,cap,32], frames per extractor)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    F, h, w = frames.shape
+    cap = extractors[0].max_keypoints(w, h)
+    kps = np.zeros((F, cap), KP_DTYPE)
+    desc = np.zeros((F, cap, 32), np.uint8)
+    counts = np.zeros((F, 2), np.int32)
+    per = extract_batch_multi_raw(extractors, frames.ctypes.data, F, w, h, w, w * h, vLappingArea, kps.ctypes.data, desc.ctypes.data, cap,
+                                  counts.ctypes.data)
+    return counts, kps, desc, per
 
 
 def stereo_match(left, right, keys_l, desc_l, keys_r, desc_r, mb, mbf):

@@ -26,7 +26,7 @@ const int kEdge = 19;  // EDGE_THRESHOLD, reference :72
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mpHandle(nullptr), mnDevice(0), mbDownloadPyramid(true) {
+      mpHandle(nullptr), mnDevice(0), mbDownloadPyramid(true), mpPyramidHost(nullptr), mnPyramidHostBytes(0) {
     if (const char* env = std::getenv("ORBX_DEVICE")) mnDevice = std::atoi(env);
     // Constructor tables (reference :419-474): plain host arithmetic through the library's device-free entry point, so the
     // accessors are right even when no GPU is present -- ORB-SLAM3 constructs extractors while parsing its settings
@@ -54,6 +54,8 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 }
 
 ORBextractor::~ORBextractor() {
+    mvImagePyramid.clear();
+    if (mpPyramidHost) orbx_host_free(mpPyramidHost);
     if (mpHandle) orbx_destroy(mpHandle);
 }
 
@@ -85,13 +87,28 @@ bool ORBextractor::EnsureHandle() {
     return true;
 }
 
+// mvImagePyramid (reference :1173-1177): ONE device-to-host copy of the frame's whole bordered block into a pinned buffer the
+// extractor owns and reuses; the level Mats are headers into it (ROI at (19,19) of a (w+38) x (h+38) plane whose row step is
+// the device pitch), valid until the next call that rebuilds the pyramid -- the reference also replaces them on every call.
 bool ORBextractor::DownloadPyramid() {
+    int w0 = 0, h0 = 0;
+    if (orbx_get_level_size(mpHandle, 0, &w0, &h0) != ORBX_OK) return false;
+    size_t bytes = 0;
+    std::vector<size_t> off((size_t)nlevels);
+    std::vector<int32_t> pitch((size_t)nlevels), lw((size_t)nlevels), lh((size_t)nlevels);
+    if (orbx_get_pyramid_layout(mpHandle, w0, h0, &bytes, off.data(), pitch.data(), lw.data(), lh.data()) != ORBX_OK) return false;
+    if (bytes > mnPyramidHostBytes) {
+        for (int l = 0; l < nlevels; ++l) mvImagePyramid[l] = cv::Mat();   // headers into the old buffer
+        orbx_host_free(mpPyramidHost);
+        mpPyramidHost = static_cast<unsigned char*>(orbx_host_alloc(bytes, 0));
+        mnPyramidHostBytes = mpPyramidHost ? bytes : 0;
+        if (!mpPyramidHost) return false;
+    }
+    if (orbx_download_pyramid(mpHandle, 0, mpPyramidHost, mnPyramidHostBytes) != ORBX_OK) return false;
     for (int l = 0; l < nlevels; ++l) {
-        int w = 0, h = 0;
-        if (orbx_get_level_size(mpHandle, l, &w, &h) != ORBX_OK) return false;
-        cv::Mat temp(cv::Size(w + 2 * kEdge, h + 2 * kEdge), CV_8UC1);                    // reference :1173-1175
-        if (orbx_get_pyramid_level(mpHandle, 0, l, temp.data, temp.step, 1) != ORBX_OK) return false;
-        mvImagePyramid[l] = temp(cv::Rect(kEdge, kEdge, w, h));                          // :1177
+        unsigned char* plane = mpPyramidHost + off[(size_t)l] + (ORBX_PLANE_PADL - kEdge);      // byte of border column -19 in plane row 0
+        cv::Mat temp(lh[(size_t)l] + 2 * kEdge, lw[(size_t)l] + 2 * kEdge, CV_8UC1, plane, (size_t)pitch[(size_t)l]);
+        mvImagePyramid[l] = temp(cv::Rect(kEdge, kEdge, lw[(size_t)l], lh[(size_t)l]));   // :1177
     }
     return true;
 }

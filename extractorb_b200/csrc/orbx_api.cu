@@ -12,8 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <utility>
 #include <vector>
@@ -51,14 +53,13 @@ struct PlanEntry {
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
-    int rs_split_x[ORBX_MAX_LEVELS] = {0};  // extent of the second-to-last tile when the last two share the remainder, else 0
-    int rs_split_y[ORBX_MAX_LEVELS] = {0};
     // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
     struct GraphKey {
         const void* imgs; long long rs, fs; int nf, lap0, lap1; void* kps; void* desc; int cap; void* counts; int fo, stages;
+        bool border;          // the graph includes k_pyr_border (one or two frames, or a pyramid sink is set)
         bool operator==(const GraphKey& o) const {
             return imgs == o.imgs && rs == o.rs && fs == o.fs && nf == o.nf && lap0 == o.lap0 && lap1 == o.lap1 && kps == o.kps &&
-                   desc == o.desc && cap == o.cap && counts == o.counts && fo == o.fo && stages == o.stages;
+                   desc == o.desc && cap == o.cap && counts == o.counts && fo == o.fo && stages == o.stages && border == o.border;
         }
     };
     struct GraphSlot { GraphKey key; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
@@ -81,6 +82,8 @@ struct OrbxHandle {
     int umax[16];
     OrbxFloatConsts fc;
     int cand_per_cell = 64;
+    int n_slots = 4;               // staging slots of the host-buffer pipeline (ORBX_SLOTS=2..4)
+    bool ramp = true;              // ramp the launch-group size of host-buffer calls up / down (ORBX_RAMP=0 disables)
     bool fast_v1 = false;          // ORBX_FAST_V1=1: the round-1 warp-per-cell FAST kernel (A/B measurements only)
     // plans keyed by image size
     std::map<std::pair<int, int>, PlanEntry*> plans;
@@ -93,6 +96,7 @@ struct OrbxHandle {
     OrbxWs ws2{};                  // workspace set 1: consecutive launch groups alternate sets and compute streams
     int ws2_frames = 0;
     int res_set = 0;               // which set holds the resident (last) group
+    bool borders_valid[2] = {false, false};   // the resident planes of each set have their 19-px border (k_pyr_border ran)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_s2 = nullptr;
     cudaStream_t s_side = nullptr;      // side branch of captured graphs: border + blur run beside FAST + quadtree
@@ -106,6 +110,9 @@ struct OrbxHandle {
     void* d_out = nullptr; size_t d_out_bytes = 0;          // output staging (two slots)
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
     int* h_flag = nullptr;                                  // pinned copy of the overflow flag word
+    uint8_t* pyr_out = nullptr; size_t pyr_out_stride = 0;  // orbx_set_pyramid_output: host sink of every frame's bordered pyramid
+    cudaEvent_t ev_pyr_ready[2] = {nullptr, nullptr}, ev_pyr_done[2] = {nullptr, nullptr};
+    bool pyr_pending[2] = {false, false};
     uint8_t* d_stereo = nullptr; size_t d_stereo_bytes = 0;  // scratch of orbx_stereo_match / orbx_frame_* / orbx_search_for_initialization
     uint8_t* d_frame = nullptr; size_t d_frame_bytes = 0;    // device-resident outputs of orbx_extract_frame
     uint8_t* h_out1 = nullptr; size_t h_out1_bytes = 0;      // pinned read-back buffer of single-frame host calls
@@ -221,22 +228,6 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
     }
 }
 
-// Host twins of rs_tile_span (orbx_kernels.cuh): the resize kernel's tile grid along one axis.
-int rs_axis_split(int len, int full, int align) {
-    const int nb = (len + full - 1) / full, rem = len % full;
-    if (nb < 2 || rem == 0 || rem >= ORBX_RS_MIN_EDGE) return 0;
-    const int left = len - (nb - 2) * full;                   // what the last two tiles share: full + rem
-    return (int)align_up((left + 1) / 2, align);
-}
-void rs_host_span(int b, int nb, int full, int len, int split, int& o, int& n) {
-    o = b * full;
-    n = std::min(full, len - o);
-    if (split > 0) {
-        if (b == nb - 2) n = split;
-        else if (b == nb - 1) { o = (nb - 2) * full + split; n = len - o; }
-    }
-}
-
 void free_plan(PlanEntry* p) {
     if (!p) return;
     for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -255,7 +246,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.min_th = std::min(std::max(h->prm.min_th_fast, 0), 255);
     for (int i = 0; i < 16; ++i) P.umax[i] = h->umax[i];
     long long plane_off = 0, blur_off = 0, cand_off = 0;
-    int kp_off = 0, maxcw = 7, maxch = 7, qt_nc = 8, ft_maxtw = 7, ft_maxth = 7, ft_qcap = 1;
+    int kp_off = 0, maxcw = 7, maxch = 7, qt_nc = 8, ft_maxtw = 7, ft_maxth = 7, ft_qcap = 1, ft_scap = 1;
     for (int l = 0; l < L; ++l) {
         OrbxLevel& V = P.lv[l];
         V.w = cv_round_f((float)width * h->inv_sf[l]);     // :1171
@@ -280,23 +271,16 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 linear_axis_table(S.w, V.w, pe->xtab);
                 linear_axis_table(S.h, V.h, pe->ytab);
             }
-            // tile grid of the resize kernel (k_pyr_resize: rs_tile_span) and the exact maxima of its shared-memory source window
-            pe->rs_split_x[l] = rs_axis_split(V.w, ORBX_RS_TW, 4);
-            pe->rs_split_y[l] = rs_axis_split(V.h, ORBX_RS_TH, 1);
+            // shared-memory window of the resize kernel: exact maxima over its 128x64 tiles (the 16-row tiles of the latency
+            // instance are subsets of them)
             int rows = 1, cols = 1;
-            for (int pass = 0; pass < 2; ++pass) {          // pass 0: plain grid (latency instance, subsets of 64-row tiles), pass 1: split grid
-                const int sx = pass ? pe->rs_split_x[l] : 0, sy = pass ? pe->rs_split_y[l] : 0;
-                const int nby = (V.h + ORBX_RS_TH - 1) / ORBX_RS_TH, nbx = (V.w + ORBX_RS_TW - 1) / ORBX_RS_TW;
-                for (int b = 0; b < nby; ++b) {
-                    int o, n;
-                    rs_host_span(b, nby, ORBX_RS_TH, V.h, sy, o, n);
-                    rows = std::max(rows, std::min(pe->ytab[V.ytab_off + o + n - 1].x + 1, S.h - 1) - pe->ytab[V.ytab_off + o].x + 1);
-                }
-                for (int b = 0; b < nbx; ++b) {
-                    int o, n;
-                    rs_host_span(b, nbx, ORBX_RS_TW, V.w, sx, o, n);
-                    cols = std::max(cols, std::min(pe->xtab[V.xtab_off + o + n - 1].x + 1, S.w - 1) - pe->xtab[V.xtab_off + o].x + 1);
-                }
+            for (int y0 = 0; y0 < V.h; y0 += ORBX_RS_TH) {
+                const int yl = std::min(y0 + ORBX_RS_TH, V.h) - 1;
+                rows = std::max(rows, std::min(pe->ytab[V.ytab_off + yl].x + 1, S.h - 1) - pe->ytab[V.ytab_off + y0].x + 1);
+            }
+            for (int x0 = 0; x0 < V.w; x0 += ORBX_RS_TW) {
+                const int xl = std::min(x0 + ORBX_RS_TW, V.w) - 1;
+                cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
             }
             pe->rs_rows[l] = rows;
             pe->rs_pitch[l] = (int)align_up(cols + 15 + 15, 16);     // 16-byte aligned window start + whole 16-byte vectors
@@ -366,10 +350,12 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 T.pq0 = (uint8_t)pq0; T.npairs = (uint8_t)npairs;
                 T.pmagic = 0xffffffffu / (unsigned)npairs + 1u;
                 T.nitems = (uint16_t)(npairs * (T.th - 6));
-                auto spread8 = [](unsigned m) {
-                    return (m & 1u) | ((m & 2u) << 15) | ((m & 4u) >> 1) | ((m & 8u) << 14) | ((m & 0x10u) >> 2) | ((m & 0x20u) << 13) |
-                           ((m & 0x40u) >> 3) | ((m & 0x80u) << 12);
+                auto spread8 = [](unsigned m) {                               // pixel k of a pair -> bit 8k+7 (k < 4), 8(k-4)+3 (k >= 4)
+                    unsigned sp = 0;
+                    for (int k = 0; k < 8; ++k) sp |= ((m >> k) & 1u) << (k < 4 ? 8 * k + 7 : 8 * (k - 4) + 3);
+                    return sp;
                 };
+                T.vmagic = 0xffffffffu / (unsigned)((a16 + T.tw + 15) >> 4) + 1u;
                 T.first_mask = spread8((0xffu << (lo - 8 * pq0)) & 0xffu);
                 T.last_mask = spread8(0xffu >> (8 * pq1 + 7 - hi));
                 for (int c = 0; c < nc; ++c) {                                // the layout k_fast_tiles relies on
@@ -382,6 +368,8 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 pe->tiles.push_back(T);
                 ft_maxtw = std::max(ft_maxtw, (int)T.tw); ft_maxth = std::max(ft_maxth, (int)T.th);
                 ft_qcap = std::max(ft_qcap, (T.tw - 6) * (T.th - 6));
+                // strict 3x3 maxima inside a cell: at most one per 2x2 block of its interior
+                ft_scap = std::max(ft_scap, nc * ((V.wCell + 1) / 2) * ((T.th - 6 + 1) / 2));
                 j0 += nc;
             }
         }
@@ -418,10 +406,12 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.ft_tp = (int)align_up(15 + ft_maxtw + 12, 16);       // alignment slack + the word right of the last pair
     P.ft_trows = ft_maxth;
     P.ft_qcap = (int)align_up(ft_qcap, 8);
-    pe->ft_smem = 2 * (size_t)P.ft_tp * P.ft_trows + 2 * (size_t)P.ft_qcap;
+    P.ft_scap = (int)align_up(ft_scap, 8);
+    P.ft_tpmagic = 0xffffffffu / (unsigned)P.ft_tp + 1u;
+    pe->ft_smem = 2 * (size_t)P.ft_tp * P.ft_trows + 2 * (size_t)P.ft_qcap + 2 * (size_t)P.ft_scap;
     if (pe->ft_smem > 200 * 1024 || (long long)P.ft_tp * P.ft_trows > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
     {   // p / ft_tp by __umulhi in k_fast_tiles: exact over the tile's byte range
-        const unsigned m = 0xffffffffu / (unsigned)P.ft_tp + 1u;
+        const unsigned m = P.ft_tpmagic;
         for (unsigned pp = 0; pp < (unsigned)(P.ft_tp * P.ft_trows); ++pp)
             if ((unsigned)(((unsigned long long)pp * m) >> 32) != pp / (unsigned)P.ft_tp) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "internal: tile pitch magic"); }
     }
@@ -536,6 +526,15 @@ enum { STAGES_PYRAMID = 1, STAGES_KEYPOINTS = 2, STAGES_ALL = 3 };
 // dynamic shared memory of k_pyr_resize: staged source window + 16-bit horizontal sums + destination-row descriptors
 size_t rs_smem_bytes(int rows, int pitch) { return (size_t)rows * pitch + (size_t)rows * ORBX_RS_TW * 2 + (size_t)ORBX_RS_TH * 16; }
 
+int launch_border(OrbxHandle* h, PlanEntry* pe, const OrbxWs& ws, int nf, cudaStream_t st) {
+    const OrbxPlan& P = pe->plan;
+    int max_rows = 0;
+    for (int l = 0; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
+    k_pyr_border<<<dim3((max_rows + ORBX_BORDER_ROWS - 1) / ORBX_BORDER_ROWS, P.nlevels, nf), dim3(16, 16), 0, st>>>(P, ws);
+    (void)h;
+    return ORBX_OK;
+}
+
 // Launch the stages for `nf` device-resident frames.  Outputs (device pointers, may be NULL) are written
 // at frame index frame_out0 + f.
 int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d_imgs, long long row_stride,
@@ -589,7 +588,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         {
             const OrbxLevel& V = P.lv[0];
             const dim3 blk(32, 8);
-            const dim3 grd((V.pitch / 16 + 31) / 32, (V.plane_rows + 7) / 8, nf);     // whole plane: level 0 and its border in one pass
+            const dim3 grd(((V.w + 15) / 16 + 31) / 32, (V.h + 7) / 8, nf);
             const int aligned16 = ((uintptr_t)d_imgs % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0) ? 1 : 0;
             k_pyr_level0<<<grd, blk, 0, st>>>(P, ws, d_imgs, row_stride, frame_stride, aligned16);
             ++launches;
@@ -605,14 +604,13 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             const int pitch = fixed ? ORBX_RS_PITCH : pe->rs_pitch[l];
             const size_t smem = rs_smem_bytes(pe->rs_rows[l], pitch);
             if (lat) {
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
-                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, -1, -1);
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             } else {
-                const int sx = pe->rs_split_x[l], sy = pe->rs_split_y[l];
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
-                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, sx, sy);
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             }
             ++launches;
             if (per_level) { const int rb = level_branch(l); if (rb != ORBX_OK) return rb; }
@@ -626,14 +624,15 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             ORBX_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
             sb = h->s_side;
         }
-        if (nf <= 2 && P.nlevels > 1) {
-            // latency instance (16-row resize tiles): borders of levels >= 1 by their own kernel, on the side branch.  The
-            // throughput instance writes them from the resize tiles that produce the edge pixels; level 0 always has its own.
-            int max_rows = 0;
-            for (int l = 1; l < P.nlevels; ++l) max_rows = std::max(max_rows, P.lv[l].plane_rows);
-            k_pyr_border<<<dim3((max_rows + ORBX_BORDER_ROWS - 1) / ORBX_BORDER_ROWS, P.nlevels - 1, nf), dim3(16, 16), 0, sb>>>(P, ws);
+        // The 19-px border is read by nobody on this path (k_pyr_border): it is written here only for one or two frames (the
+        // drop-in operator() hands mvImagePyramid to its caller; off the critical path on the side branch) and when a pyramid
+        // sink is set; otherwise on demand, by the accessors that take planes out of the device (ensure_borders).
+        const bool want_border = nf <= 2 || h->pyr_out != nullptr;
+        if (want_border) {
+            launch_border(h, pe, ws, nf, sb);
             ++launches;
         }
+        h->borders_valid[set] = want_border;
         if (fork) {
             k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, sb>>>(P, ws, 0);
             ++launches;
@@ -707,12 +706,14 @@ int launch_group(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_t* d
     if (!use_graph)
         return launch_group_raw(h, pe, st, d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts,
                                 frame_out0, stages, false, set);
-    const PlanEntry::GraphKey key{d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts, frame_out0, stages};
+    const bool border = (stages & STAGES_PYRAMID) && (nf <= 2 || h->pyr_out != nullptr);
+    const PlanEntry::GraphKey key{d_imgs, row_stride, frame_stride, nf, lap0, lap1, d_kps, d_desc, cap_per_frame, d_counts, frame_out0, stages, border};
     for (auto& g : pe->graphs)
         if (g.exec && g.key == key) {
             ORBX_CUDA(cudaGraphLaunch(g.exec, st));
             h->stage_launches += g.launches; h->total_launches += g.launches;
             h->cur = pe; h->resident_frames = nf; h->res_set = 0;
+            if (stages & STAGES_PYRAMID) h->borders_valid[0] = border;
             return ORBX_OK;
         }
     cudaGraph_t graph = nullptr;
@@ -823,6 +824,16 @@ int check_overflow(OrbxHandle* h, bool* overflow, cudaStream_t st) {
 
 static const OrbxWs& res_ws(const OrbxHandle* h) { return h->res_set ? h->ws2 : h->ws; }
 
+// mvImagePyramid leaves the device with its border (reference :1173-1177, :1193): written now if the extraction skipped it.
+static int ensure_borders(OrbxHandle* h) {
+    if (!h->cur || h->resident_frames < 1 || h->borders_valid[h->res_set]) return ORBX_OK;
+    launch_border(h, h->cur, res_ws(h), h->resident_frames, h->stream);
+    h->total_launches += 1; h->stage_launches += 1;
+    ORBX_CUDA(cudaGetLastError());
+    h->borders_valid[h->res_set] = true;
+    return ORBX_OK;
+}
+
 extern "C" {
 
 const char* orbx_status_string(int s) {
@@ -859,6 +870,8 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     h->cand_per_cell = prm->cand_per_cell > 0 ? prm->cand_per_cell : 64;
     h->device = device;
     if (const char* e1 = getenv("ORBX_FAST_V1")) h->fast_v1 = atoi(e1) != 0;
+    if (const char* e2 = getenv("ORBX_SLOTS")) h->n_slots = std::min(4, std::max(2, atoi(e2)));
+    if (const char* e3 = getenv("ORBX_RAMP")) h->ramp = atoi(e3) != 0;
     build_ctor_tables(h);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -872,6 +885,10 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
         e = cudaStreamCreateWithFlags(&h->s_lvl[l], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_lvl_ready[l], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_lvl_done[l], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_pyr_ready[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr_done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
@@ -927,6 +944,10 @@ void orbx_destroy(OrbxHandle* h) {
         if (h->ev_in_free[i]) cudaEventDestroy(h->ev_in_free[i]);
     }
     if (h->h_flag) cudaFreeHost(h->h_flag);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_pyr_ready[i]) cudaEventDestroy(h->ev_pyr_ready[i]);
+        if (h->ev_pyr_done[i]) cudaEventDestroy(h->ev_pyr_done[i]);
+    }
     if (h->ev_s2) cudaEventDestroy(h->ev_s2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -982,126 +1003,255 @@ int orbx_max_keypoints(const OrbxHandle* hc, int width, int height) {
     return pe->plan.kp_total;
 }
 
+}  // extern "C"
+
+namespace {
+
+// The frames of one call, handed out in launch groups.  One consumer (orbx_extract_batch) walks them in order; several
+// consumers (orbx_extract_batch_multi: one host thread + handle per device) pull groups from the shared cursor, so a
+// device that is fed more slowly (GPUs behind a shared PCIe switch get unequal shares) simply takes fewer groups and all
+// devices finish together.
+struct FramePool {
+    std::atomic<int> cursor{0};
+    int n_frames = 0;
+    int consumers = 1;
+};
+
+// Next launch group for a consumer that has already taken `gi` groups.  Host-buffer pipelines ramp the group size up at
+// the start of the call and down at its end, so that the first H2D copy (nothing to overlap with yet) and the last
+// kernels + D2H copy (nothing left to overlap) are short.  Never more than `group` frames: that is what the workspace
+// and the staging slots hold.
+int next_group(FramePool& pool, int group, int gi, bool ramp, int* f0_out) {
+    int f0 = pool.cursor.load(std::memory_order_relaxed);
+    for (;;) {
+        const int remaining = pool.n_frames - f0;
+        if (remaining <= 0) return 0;
+        int nf = std::min(group, remaining);
+        if (ramp && group > 32) {
+            const int up = gi < 4 ? (32 << gi) : group;
+            nf = std::min(nf, up);
+            const int share = (remaining + pool.consumers - 1) / pool.consumers;       // what is left for this consumer
+            if (share <= group) nf = std::min(nf, std::max(32, (share + 1) / 2));
+            if (remaining - nf < 16 && remaining <= group) nf = remaining;             // no tiny tail group
+        }
+        if (pool.cursor.compare_exchange_weak(f0, f0 + nf, std::memory_order_relaxed)) { *f0_out = f0; return nf; }
+    }
+}
+
+struct BatchArgs {
+    const uint8_t* images; int in_mem; int n_frames; int width, height; size_t row_stride, frame_stride; int lap0, lap1;
+    OrbxKeyPoint* kps; uint8_t* desc; int cap_per_frame; int32_t* counts; int out_mem;
+};
+
+// One pass of a consumer over the pool.  *overflow: some frame overflowed its FAST-candidate workspace (the caller regrows
+// and repeats the call); *taken: frames this consumer processed.
+int extract_pass(OrbxHandle* h, FramePool& pool, const BatchArgs& a, cudaStream_t st, bool* overflow, int* taken) {
+    *overflow = false;
+    *taken = 0;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int n_frames = a.n_frames, width = a.width, height = a.height, cap_per_frame = a.cap_per_frame;
+    PlanEntry* pe = nullptr;
+    int rc = get_plan(h, width, height, &pe);
+    if (rc != ORBX_OK) return rc;
+    const int group = std::min(h->prm.max_batch, n_frames);
+    const bool multi_group = n_frames > group || pool.consumers > 1;
+    // Consecutive launch groups alternate between two workspace sets and two compute streams, so that the
+    // latency-bound kernels and the tail of every kernel of one group overlap the next group's kernels.
+    // (Profiled runs stay on one stream: their per-stage event times must not overlap.)
+    const bool dual = n_frames > group && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_SINGLE_STREAM);
+    rc = ensure_workspace(h, pe, group, dual ? 2 : 1);
+    if (rc != ORBX_OK) return rc;
+    rc = set_kernel_attrs(h, pe);
+    if (rc != ORBX_OK) return rc;
+    // Host buffers are pipelined through staging slots: copy-in (s_in), kernels (st / stream2), copy-out (s_out).
+    const bool host_in = a.in_mem == ORBX_MEM_HOST, host_out = a.out_mem == ORBX_MEM_HOST;
+    const bool copy_only = (h->prm.flags & ORBX_FLAG_COPY_ONLY) != 0;
+    const size_t kp_bytes = (size_t)cap_per_frame * sizeof(OrbxKeyPoint), ds_bytes = (size_t)cap_per_frame * 32;
+    const size_t in_slot = (size_t)align_up((long long)width * height * group, 256);
+    const size_t o_kps_off = 0, o_desc_off = (size_t)align_up((long long)kp_bytes * group, 256);
+    const size_t o_cnt_off = o_desc_off + (size_t)align_up((long long)ds_bytes * group, 256);
+    const size_t out_slot = o_cnt_off + (size_t)align_up(8ll * group, 256);
+    const int n_out_slots = multi_group ? h->n_slots : 1;
+    if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, (size_t)n_out_slots * out_slot, false); if (rc != ORBX_OK) return rc; }
+    const bool single_out = host_out && n_frames == 1;
+    if (single_out) { rc = ensure_bytes(h, (void**)&h->h_out1, &h->h_out1_bytes, out_slot, true); if (rc != ORBX_OK) return rc; }
+    const int n_in_slots = multi_group ? h->n_slots : 1;
+    if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)n_in_slots * in_slot, false); if (rc != ORBX_OK) return rc; }
+    const bool ramp = (host_in || host_out) && h->ramp;
+    OrbxKeyPoint* kps = a.kps; uint8_t* desc = a.desc; int32_t* counts = a.counts;
+    const uint8_t* images = a.images;
+    for (int gi = 0;; ++gi) {
+        int f0 = 0;
+        const int nf = next_group(pool, group, gi, ramp, &f0);
+        if (nf == 0) break;
+        *taken += nf;
+        const int slot = gi & 1;
+        const int set = dual ? slot : 0;
+        cudaStream_t cs = set ? h->stream2 : st;
+        const uint8_t* d_imgs;
+        long long rs, fs;
+        const int islot = gi % n_in_slots;
+        if (host_in) {
+            uint8_t* dst = h->d_in + (size_t)islot * in_slot;
+            if (gi >= n_in_slots) ORBX_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_in_free[islot], 0));   // slot's previous group consumed
+            if (a.row_stride == (size_t)width && (nf == 1 || a.frame_stride == (size_t)width * height)) {
+                ORBX_CUDA(cudaMemcpyAsync(dst, images + (size_t)f0 * a.frame_stride, (size_t)width * height * nf, cudaMemcpyHostToDevice, h->s_in));
+            } else {
+                for (int f = 0; f < nf; ++f)
+                    ORBX_CUDA(cudaMemcpy2DAsync(dst + (size_t)f * width * height, (size_t)width, images + (size_t)(f0 + f) * a.frame_stride,
+                                                a.row_stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->s_in));
+            }
+            ORBX_CUDA(cudaEventRecord(h->ev_h2d[islot], h->s_in));
+            ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_h2d[islot], 0));
+            d_imgs = dst; rs = width; fs = (long long)width * height;
+        } else {
+            d_imgs = images + (size_t)f0 * a.frame_stride; rs = (long long)a.row_stride; fs = (long long)a.frame_stride;
+        }
+        // pyramid sink (orbx_set_pyramid_output): this workspace set's previous pyramids must have left before they are overwritten
+        if (h->pyr_out && h->pyr_pending[set]) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_pyr_done[set], 0));
+        if (host_out) {
+            const int oslot = gi % n_out_slots;
+            uint8_t* ob = (uint8_t*)h->d_out + (size_t)oslot * out_slot;
+            if (gi >= n_out_slots) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[oslot], 0));   // slot's previous results copied out
+            if (!copy_only) {
+                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, a.lap0, a.lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
+                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set, !multi_group);
+                if (rc != ORBX_OK) return rc;
+            }
+            ORBX_CUDA(cudaEventRecord(h->ev_done[oslot], cs));
+            if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
+            ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[oslot], 0));
+            if (single_out) {
+                // one frame: a single read-back into pinned memory; the caller's (usually pageable) arrays are filled after
+                // the final synchronisation -- three copies into pageable memory would block the host one after the other
+                ORBX_CUDA(cudaMemcpyAsync(h->h_out1, ob, out_slot, cudaMemcpyDeviceToHost, h->s_out));
+            } else {
+                if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
+                if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
+            }
+            ORBX_CUDA(cudaEventRecord(h->ev_d2h[oslot], h->s_out));
+        } else {
+            if (!copy_only) {
+                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, a.lap0, a.lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set, !multi_group);
+                if (rc != ORBX_OK) return rc;
+            }
+            if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
+        }
+        if (h->pyr_out && !copy_only) {
+            // mvImagePyramid to the host (reference :1173-1177 leaves it there): the group's bordered planes, one copy
+            const OrbxWs& w = set ? h->ws2 : h->ws;
+            ORBX_CUDA(cudaEventRecord(h->ev_pyr_ready[set], cs));
+            ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_pyr_ready[set], 0));
+            ORBX_CUDA(cudaMemcpy2DAsync(h->pyr_out + (size_t)f0 * h->pyr_out_stride, h->pyr_out_stride, w.pyr, (size_t)pe->pyr_stride,
+                                        std::min((size_t)pe->pyr_stride, h->pyr_out_stride), (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
+            ORBX_CUDA(cudaEventRecord(h->ev_pyr_done[set], h->s_out));
+            h->pyr_pending[set] = true;
+        }
+    }
+    if (dual) {   // join the second compute stream into the caller's stream
+        ORBX_CUDA(cudaEventRecord(h->ev_s2, h->stream2));
+        ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_s2, 0));
+    }
+    rc = fetch_overflow(h, st);
+    if (rc != ORBX_OK) return rc;
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    if (host_out || h->pyr_out) ORBX_CUDA(cudaStreamSynchronize(h->s_out));
+    h->pyr_pending[0] = h->pyr_pending[1] = false;
+    if (single_out && *taken == 1) {
+        int32_t c2[2];
+        std::memcpy(c2, h->h_out1 + o_cnt_off, 8);
+        const size_t nk = (size_t)std::min(std::max(c2[0], 0), cap_per_frame);     // entries beyond n are unspecified padding
+        if (kps) std::memcpy(kps, h->h_out1 + o_kps_off, nk * sizeof(OrbxKeyPoint));
+        if (desc) std::memcpy(desc, h->h_out1 + o_desc_off, nk * 32);
+        if (counts) std::memcpy(counts, c2, 8);
+    }
+    if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
+    return check_overflow(h, overflow, st);
+}
+
+int check_batch_args(OrbxHandle* h, const BatchArgs& a) {
+    if (!a.images || a.width <= 0 || a.height <= 0 || a.n_frames <= 0) return fail(h, ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (a.row_stride < (size_t)a.width || a.cap_per_frame < 0 || (a.n_frames > 1 && a.frame_stride < a.row_stride * (size_t)a.height))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad strides or capacity");
+    return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height,
                        size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps, uint8_t* desc,
                        int cap_per_frame, int32_t* counts, int out_mem, void* stream) {
     if (!h) return ORBX_ERR_BAD_ARGUMENT;
-    if (!images || width <= 0 || height <= 0 || n_frames <= 0) return fail(h, ORBX_ERR_EMPTY_IMAGE, "empty image");
-    if (row_stride < (size_t)width || cap_per_frame < 0 || (n_frames > 1 && frame_stride < row_stride * (size_t)height))
-        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad strides or capacity");
+    const BatchArgs a{images, in_mem, n_frames, width, height, row_stride, frame_stride, lap0, lap1, kps, desc, cap_per_frame, counts, out_mem};
+    int rc = check_batch_args(h, a);
+    if (rc != ORBX_OK) return rc;
     ORBX_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     for (int attempt = 0;; ++attempt) {
-        PlanEntry* pe = nullptr;
-        int rc = get_plan(h, width, height, &pe);
-        if (rc != ORBX_OK) return rc;
-        const int group = std::min(h->prm.max_batch, n_frames);
-        // Consecutive launch groups alternate between two workspace sets and two compute streams, so that the
-        // latency-bound kernels and the tail of every kernel of one group overlap the next group's kernels.
-        // (Profiled runs stay on one stream: their per-stage event times must not overlap.)
-        const bool dual = n_frames > group && !(h->prm.flags & ORBX_FLAG_PROFILE) && !(h->prm.flags & ORBX_FLAG_SINGLE_STREAM);
-        rc = ensure_workspace(h, pe, group, dual ? 2 : 1);
-        if (rc != ORBX_OK) return rc;
-        rc = set_kernel_attrs(h, pe);
-        if (rc != ORBX_OK) return rc;
-        // Host buffers are pipelined through two staging slots: copy-in (s_in), kernels (st), copy-out (s_out).
-        const bool host_in = in_mem == ORBX_MEM_HOST, host_out = out_mem == ORBX_MEM_HOST;
-        const size_t kp_bytes = (size_t)cap_per_frame * sizeof(OrbxKeyPoint), ds_bytes = (size_t)cap_per_frame * 32;
-        const size_t in_slot = (size_t)align_up((long long)width * height * group, 256);
-        const size_t o_kps_off = 0, o_desc_off = (size_t)align_up((long long)kp_bytes * group, 256);
-        const size_t o_cnt_off = o_desc_off + (size_t)align_up((long long)ds_bytes * group, 256);
-        const size_t out_slot = o_cnt_off + (size_t)align_up(8ll * group, 256);
-        const int n_out_slots = n_frames > group ? 4 : 1;
-        if (host_out) { rc = ensure_bytes(h, &h->d_out, &h->d_out_bytes, (size_t)n_out_slots * out_slot, false); if (rc != ORBX_OK) return rc; }
-        const bool single_out = host_out && n_frames == 1;
-        if (single_out) { rc = ensure_bytes(h, (void**)&h->h_out1, &h->h_out1_bytes, out_slot, true); if (rc != ORBX_OK) return rc; }
-        const int n_in_slots = n_frames > group ? 4 : 1;
-        if (host_in) { rc = ensure_bytes(h, (void**)&h->d_in, &h->d_in_bytes, (size_t)n_in_slots * in_slot, false); if (rc != ORBX_OK) return rc; }
-        int gi = 0;
-        for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++gi) {
-            nf = std::min(group, n_frames - f0);
-            if ((host_in || host_out) && group > 32) {
-                // Host buffers: ramp the group size up at the start of the call and down at its end, so that the first
-                // H2D copy (nothing to overlap with yet) and the last kernels + D2H copy (nothing left to overlap) are short.
-                const int up = gi < 4 ? (32 << gi) : group;
-                const int remaining = n_frames - f0;
-                nf = std::min(nf, up);
-                if (remaining <= group) nf = std::min(nf, std::max(32, (remaining + 1) / 2));
-                if (remaining - nf < 16 && remaining <= group) nf = remaining;   // no tiny tail group -- but never more than the workspace holds
-            }
-            const int slot = gi & 1;
-            const int set = dual ? slot : 0;
-            cudaStream_t cs = set ? h->stream2 : st;
-            const uint8_t* d_imgs;
-            long long rs, fs;
-            const int islot = gi % n_in_slots;
-            if (host_in) {
-                uint8_t* dst = h->d_in + (size_t)islot * in_slot;
-                if (gi >= n_in_slots) ORBX_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_in_free[islot], 0));   // slot's previous group consumed
-                if (row_stride == (size_t)width && (nf == 1 || frame_stride == (size_t)width * height)) {
-                    ORBX_CUDA(cudaMemcpyAsync(dst, images + (size_t)f0 * frame_stride, (size_t)width * height * nf, cudaMemcpyHostToDevice, h->s_in));
-                } else {
-                    for (int f = 0; f < nf; ++f)
-                        ORBX_CUDA(cudaMemcpy2DAsync(dst + (size_t)f * width * height, (size_t)width, images + (size_t)(f0 + f) * frame_stride,
-                                                    row_stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->s_in));
-                }
-                ORBX_CUDA(cudaEventRecord(h->ev_h2d[islot], h->s_in));
-                ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_h2d[islot], 0));
-                d_imgs = dst; rs = width; fs = (long long)width * height;
-            } else {
-                d_imgs = images + (size_t)f0 * frame_stride; rs = (long long)row_stride; fs = (long long)frame_stride;
-            }
-            if (host_out) {
-                const int oslot = gi % n_out_slots;
-                uint8_t* ob = (uint8_t*)h->d_out + (size_t)oslot * out_slot;
-                if (gi >= n_out_slots) ORBX_CUDA(cudaStreamWaitEvent(cs, h->ev_d2h[oslot], 0));   // slot's previous results copied out
-                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps ? ob + o_kps_off : nullptr, desc ? ob + o_desc_off : nullptr,
-                                  cap_per_frame, (int32_t*)(ob + o_cnt_off), 0, STAGES_ALL, set, n_frames <= group);
-                if (rc != ORBX_OK) return rc;
-                ORBX_CUDA(cudaEventRecord(h->ev_done[oslot], cs));
-                if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
-                ORBX_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[oslot], 0));
-                if (single_out) {
-                    // one frame: a single read-back into pinned memory; the caller's (usually pageable) arrays are filled after
-                    // the final synchronisation -- three copies into pageable memory would block the host one after the other
-                    ORBX_CUDA(cudaMemcpyAsync(h->h_out1, ob, out_slot, cudaMemcpyDeviceToHost, h->s_out));
-                } else {
-                    if (kps) ORBX_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ob + o_kps_off, kp_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
-                    if (desc) ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ob + o_desc_off, ds_bytes * nf, cudaMemcpyDeviceToHost, h->s_out));
-                    if (counts) ORBX_CUDA(cudaMemcpyAsync(counts + 2 * (size_t)f0, ob + o_cnt_off, 8 * (size_t)nf, cudaMemcpyDeviceToHost, h->s_out));
-                }
-                ORBX_CUDA(cudaEventRecord(h->ev_d2h[oslot], h->s_out));
-            } else {
-                rc = launch_group(h, pe, cs, d_imgs, rs, fs, nf, lap0, lap1, kps, desc, cap_per_frame, counts, f0, STAGES_ALL, set, n_frames <= group);
-                if (rc != ORBX_OK) return rc;
-                if (host_in) ORBX_CUDA(cudaEventRecord(h->ev_in_free[islot], cs));
-            }
-        }
-        if (dual) {   // join the second compute stream into the caller's stream
-            ORBX_CUDA(cudaEventRecord(h->ev_s2, h->stream2));
-            ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_s2, 0));
-        }
-        rc = fetch_overflow(h, st);
-        if (rc != ORBX_OK) return rc;
-        ORBX_CUDA(cudaStreamSynchronize(st));
-        if (host_out) ORBX_CUDA(cudaStreamSynchronize(h->s_out));
-        if (single_out) {
-            int32_t c2[2];
-            std::memcpy(c2, h->h_out1 + o_cnt_off, 8);
-            const size_t nk = (size_t)std::min(std::max(c2[0], 0), cap_per_frame);     // entries beyond n are unspecified padding
-            if (kps) std::memcpy(kps, h->h_out1 + o_kps_off, nk * sizeof(OrbxKeyPoint));
-            if (desc) std::memcpy(desc, h->h_out1 + o_desc_off, nk * 32);
-            if (counts) std::memcpy(counts, c2, 8);
-        }
-        if (h->prm.flags & ORBX_FLAG_PROFILE) { rc = collect_events(h); if (rc != ORBX_OK) return rc; }
+        FramePool pool;
+        pool.n_frames = n_frames;
         bool overflow = false;
-        rc = check_overflow(h, &overflow, st);
+        int taken = 0;
+        rc = extract_pass(h, pool, a, st, &overflow, &taken);
         if (rc != ORBX_OK) return rc;
         if (!overflow) return ORBX_OK;
         // grow the candidate workspace and run the call again (every output is rewritten)
         if (attempt >= 6) return fail(h, ORBX_ERR_CANDIDATE_OVERFLOW, "FAST candidate workspace overflow after regrowth");
         h->cand_per_cell *= 4;
         drop_plans(h);
+    }
+}
+
+// "Independent frames sharded across the GPUs of one box on per-GPU streams" from ONE process: handles[i] owns device i's
+// streams and workspace, one host thread per handle runs the same three-stream pipeline as orbx_extract_batch and pulls its
+// launch groups from a cursor shared by all of them (the reference's own concurrency is this pattern with two threads and
+// two extractor instances, src/Frame.cc:109-112).  Host buffers only: feeding several devices from host memory is the point.
+int orbx_extract_batch_multi(OrbxHandle* const* handles, int n_handles, const uint8_t* images, int n_frames, int width, int height,
+                             size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps, uint8_t* desc,
+                             int cap_per_frame, int32_t* counts, int32_t* frames_per_handle) {
+    if (!handles || n_handles < 1 || n_handles > 64) return ORBX_ERR_BAD_ARGUMENT;
+    for (int i = 0; i < n_handles; ++i) {
+        if (!handles[i]) return ORBX_ERR_BAD_ARGUMENT;
+        for (int j = 0; j < i; ++j) if (handles[j] == handles[i]) return fail(handles[0], ORBX_ERR_BAD_ARGUMENT, "the same handle twice");
+    }
+    const BatchArgs a{images, ORBX_MEM_HOST, n_frames, width, height, row_stride, frame_stride, lap0, lap1, kps, desc, cap_per_frame, counts,
+                      ORBX_MEM_HOST};
+    int rc = check_batch_args(handles[0], a);
+    if (rc != ORBX_OK) return rc;
+    for (int attempt = 0;; ++attempt) {
+        FramePool pool;
+        pool.n_frames = n_frames;
+        pool.consumers = n_handles;
+        std::vector<int> rcs((size_t)n_handles, ORBX_OK), taken((size_t)n_handles, 0);
+        std::vector<char> ovf((size_t)n_handles, 0);
+        auto work = [&](int i) {
+            bool o = false;
+            rcs[(size_t)i] = extract_pass(handles[i], pool, a, handles[i]->stream, &o, &taken[(size_t)i]);
+            ovf[(size_t)i] = o ? 1 : 0;
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_handles; ++i) th.emplace_back(work, i);
+        work(0);
+        for (auto& t : th) t.join();
+        bool overflow = false;
+        for (int i = 0; i < n_handles; ++i) {
+            if (rcs[(size_t)i] != ORBX_OK) {
+                if (i != 0) handles[0]->err = handles[i]->err;
+                return rcs[(size_t)i];
+            }
+            overflow = overflow || ovf[(size_t)i];
+            if (frames_per_handle) frames_per_handle[i] = taken[(size_t)i];
+        }
+        if (!overflow) return ORBX_OK;
+        if (attempt >= 6) return fail(handles[0], ORBX_ERR_CANDIDATE_OVERFLOW, "FAST candidate workspace overflow after regrowth");
+        for (int i = 0; i < n_handles; ++i) {
+            if (cudaSetDevice(handles[i]->device) != cudaSuccess) return fail(handles[0], ORBX_ERR_CUDA, "cudaSetDevice");
+            handles[i]->cand_per_cell *= 4;
+            drop_plans(handles[i]);
+        }
     }
 }
 
@@ -1526,6 +1676,57 @@ int orbx_clahe(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, i
 
 int orbx_last_init_fallbacks(const OrbxHandle* h) { return h ? h->last_init_fallbacks : 0; }
 
+int orbx_get_pyramid_layout(OrbxHandle* h, int width, int height, size_t* frame_bytes, size_t* plane_offset, int32_t* pitch,
+                            int32_t* level_w, int32_t* level_h) {
+    if (!h || width <= 0 || height <= 0) return ORBX_ERR_BAD_ARGUMENT;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    PlanEntry* pe = nullptr;
+    int rc = get_plan(h, width, height, &pe);
+    if (rc != ORBX_OK) return rc;
+    if (frame_bytes) *frame_bytes = (size_t)pe->pyr_stride;
+    for (int l = 0; l < pe->plan.nlevels; ++l) {
+        const OrbxLevel& V = pe->plan.lv[l];
+        if (plane_offset) plane_offset[l] = (size_t)V.plane_off;
+        if (pitch) pitch[l] = V.pitch;
+        if (level_w) level_w[l] = V.w;
+        if (level_h) level_h[l] = V.h;
+    }
+    return ORBX_OK;
+}
+
+int orbx_set_pyramid_output(OrbxHandle* h, uint8_t* host_dst, size_t frame_stride) {
+    if (!h || (host_dst && frame_stride == 0)) return ORBX_ERR_BAD_ARGUMENT;
+    h->pyr_out = host_dst;
+    h->pyr_out_stride = host_dst ? frame_stride : 0;
+    return ORBX_OK;
+}
+
+int orbx_download_pyramid(OrbxHandle* h, int frame, uint8_t* host_dst, size_t capacity) {
+    if (!h || !host_dst) return ORBX_ERR_BAD_ARGUMENT;
+    if (!h->cur || frame < 0 || frame >= h->resident_frames) return fail(h, ORBX_ERR_NO_FRAME, "frame not resident");
+    if (capacity < (size_t)h->cur->pyr_stride) return fail(h, ORBX_ERR_CAPACITY, "pyramid buffer too small (orbx_get_pyramid_layout)");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    { const int rb = ensure_borders(h); if (rb != ORBX_OK) return rb; }
+    ORBX_CUDA(cudaMemcpyAsync(host_dst, res_ws(h).pyr + (size_t)frame * res_ws(h).pyr_stride, (size_t)h->cur->pyr_stride, cudaMemcpyDeviceToHost,
+                              h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+void* orbx_host_alloc(size_t bytes, int write_combined) {
+    void* p = nullptr;
+    if (bytes == 0) return nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void orbx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int* height) {
     if (!h || !h->cur) return ORBX_ERR_NO_FRAME;
     if (level < 0 || level >= h->cur->plan.nlevels) return ORBX_ERR_BAD_ARGUMENT;
@@ -1549,6 +1750,7 @@ int orbx_get_pyramid_level(OrbxHandle* h, int frame, int level, uint8_t* dst, si
     const OrbxLevel& V = h->cur->plan.lv[level];
     const int b = with_border ? ORBX_EDGE : 0;
     const uint8_t* src = res_ws(h).pyr + (size_t)frame * res_ws(h).pyr_stride + V.plane_off + (size_t)(ORBX_EDGE - b) * V.pitch + (ORBX_PADL - b);
+    if (with_border) { rc = ensure_borders(h); if (rc != ORBX_OK) return rc; }
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     ORBX_CUDA(cudaMemcpy2D(dst, dst_stride, src, (size_t)V.pitch, (size_t)V.w + 2 * b, (size_t)V.h + 2 * b, cudaMemcpyDeviceToHost));
     return ORBX_OK;

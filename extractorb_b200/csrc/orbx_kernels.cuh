@@ -29,46 +29,22 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // =================================================================================================
 // K1  ComputePyramid.
 // =================================================================================================
-// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213).  One thread per 16-byte chunk of a PLANE row (border
-// included): chunks inside the image are 128-bit copies (when the source rows are 16-byte aligned), the chunks that touch
-// the 19-px border gather their bytes through the reflect-101 index -- the border never needs a second pass over HBM.
+// Level 0 = copyMakeBorder(image, BORDER_REFLECT_101) (:1213): this kernel copies the image into the level-0
+// ROI (16 bytes per thread; 128-bit loads when the source rows are 16-byte aligned), the 19-px border is written by k_pyr_border, and only when somebody will read it (see there).
 __global__ void __launch_bounds__(256)
 k_pyr_level0(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const uint8_t* __restrict__ imgs,
              long long row_stride, long long frame_stride, int aligned16) {
     const OrbxLevel& L = plan.lv[0];
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte chunk of the plane row; level column 0 sits at byte ORBX_PADL
-    const int pr = blockIdx.y * blockDim.y + threadIdx.y;         // plane row
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int frame = blockIdx.z;
-    const int x = 16 * chunk - ORBX_PADL;                         // level column of the chunk's first byte
-    if (pr >= L.plane_rows || x >= L.w + ORBX_EDGE || x + 16 <= -ORBX_EDGE) return;
-    const int sy = reflect101(pr - ORBX_EDGE, L.h);
-    const uint8_t* srow = imgs + (long long)frame * frame_stride + (long long)sy * row_stride;
-    uint8_t* drow = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)pr * L.pitch + 16 * chunk;
-    if (x >= 0 && x + 16 <= L.w) {
-        if (aligned16) {
-            *reinterpret_cast<uint4*>(drow) = __ldg(reinterpret_cast<const uint4*>(srow + x));
-        } else {
-            uint32_t v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                v[q] = (uint32_t)__ldg(srow + x + 4 * q) | ((uint32_t)__ldg(srow + x + 4 * q + 1) << 8) | ((uint32_t)__ldg(srow + x + 4 * q + 2) << 16) |
-                       ((uint32_t)__ldg(srow + x + 4 * q + 3) << 24);
-            *reinterpret_cast<uint4*>(drow) = make_uint4(v[0], v[1], v[2], v[3]);
-        }
+    if (x >= L.w || y >= L.h) return;
+    const uint8_t* srow = imgs + (long long)frame * frame_stride + (long long)y * row_stride + x;
+    uint8_t* drow = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + y) * L.pitch + ORBX_PADL + x;
+    if (aligned16 && x + 16 <= L.w) {
+        *reinterpret_cast<uint4*>(drow) = __ldg(reinterpret_cast<const uint4*>(srow));
     } else {
-        // chunk on the left / right edge: bytes outside [-19, w+19) are padding (written with a clamped index, never read)
-        uint32_t v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t wv = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int xx = min(max(x + 4 * q + j, -ORBX_EDGE), L.w + ORBX_EDGE - 1);
-                wv |= (uint32_t)__ldg(srow + reflect101(xx, L.w)) << (8 * j);
-            }
-            v[q] = wv;
-        }
-        *reinterpret_cast<uint4*>(drow) = make_uint4(v[0], v[1], v[2], v[3]);
+        for (int j = 0; j < 16 && x + j < L.w; ++j) drow[j] = __ldg(srow + j);
     }
 }
 
@@ -136,30 +112,16 @@ __device__ __forceinline__ void border_right_word(const uint32_t* __restrict__ s
     drow[wx] = word;
 }
 
-// Tile grid of k_pyr_resize along one axis: tiles of `full` pixels from the origin; when the remainder is shorter than
-// ORBX_RS_MIN_EDGE the last two tiles share what is left (`split` = extent of the second-to-last one, else 0), so that
-// the tile holding an edge always holds the >= 28 pixels the reflect-101 border of that edge mirrors.
-#define ORBX_RS_MIN_EDGE 32
-__device__ __forceinline__ void rs_tile_span(int b, int nb, int full, int len, int split, int& o, int& n) {
-    o = b * full;
-    n = min(full, len - o);
-    if (split > 0) {
-        if (b == nb - 2) n = split;
-        else if (b == nb - 1) { o = (nb - 2) * full + split; n = len - o; }
-    }
-}
-
 template <bool AREA, int PITCH, int TH>
 __global__ void __launch_bounds__(256)
-k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt, int split_x, int split_y) {
+k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
     extern __shared__ __align__(16) uint8_t smem_rs[];
     const int src_pitch_s = PITCH ? PITCH : src_pitch_rt;
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
     const int tid = threadIdx.x;
-    int x0, y0, tw, th;                                                   // this tile's origin and extent
-    rs_tile_span(blockIdx.x, gridDim.x, ORBX_RS_TW, L.w, split_x, x0, tw);
-    rs_tile_span(blockIdx.y, gridDim.y, TH, L.h, split_y, y0, th);
+    const int x0 = blockIdx.x * ORBX_RS_TW, y0 = blockIdx.y * TH;
+    const int tw = min(ORBX_RS_TW, L.w - x0), th = min(TH, L.h - y0);   // this tile's extent
     const int frame = blockIdx.z;
     uint8_t* fbase = ws.pyr + (long long)frame * ws.pyr_stride;
     const uint8_t* splane = fbase + S.plane_off;
@@ -264,38 +226,12 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
             }
         }
     }
-    // ---- border (copyMakeBorder BORDER_REFLECT_101, :1193): the tiles on the level's edges also write the 19-px frame next to
-    // them -- side strips of their rows, and for the top / bottom tile rows the 19 band rows above / below (their own columns,
-    // plus the strips' corners).  Every source pixel lies inside this tile (split tile grid), just written by this CTA; the
-    // border bytes are read by nobody in this launch.  split_x / split_y < 0: no border here (the latency path's 16-row tiles;
-    // k_pyr_border runs afterwards instead).
-    if (split_x < 0) return;
-    const bool left = x0 == 0, right = x0 + tw == L.w, top = y0 == 0, bottom = y0 + th == L.h;
-    if (!(left || right || top || bottom)) return;
-    __syncthreads();                                                     // this CTA's level pixels are visible to all its threads
-    {
-        uint8_t* plane = fbase + L.plane_off;
-        const int n_top = top ? ORBX_EDGE : 0, n_mid = (left || right) ? th : 0, n_bot = bottom ? ORBX_EDGE : 0;
-        const int lane = tid & 15;
-        const int rw0 = L.w >> 2, nright = ((L.w + ORBX_EDGE - 1) >> 2) - rw0 + 1;   // right-strip words (the first may straddle)
-        const int cw0 = x0 >> 2, cwn = (right ? L.w >> 2 : (x0 + tw) >> 2) - cw0;    // words of this tile fully inside the level
-        for (int idx = tid >> 4; idx < n_top + n_mid + n_bot; idx += 16) {
-            int pr, sr;                                                  // destination plane row, source level row
-            bool band = true;
-            if (idx < n_top) { pr = idx; sr = ORBX_EDGE - idx; }
-            else if (idx < n_top + n_mid) { sr = y0 + idx - n_top; pr = ORBX_EDGE + sr; band = false; }
-            else { const int j = idx - n_top - n_mid; pr = ORBX_EDGE + L.h + j; sr = L.h - 2 - j; }
-            const uint32_t* srow = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + sr) * L.pitch + ORBX_PADL);
-            uint32_t* drow = reinterpret_cast<uint32_t*>(plane + (long long)pr * L.pitch + ORBX_PADL);
-            if (band)
-                for (int wx = lane; wx < cwn; wx += 16) drow[cw0 + wx] = srow[cw0 + wx];
-            if (left && lane < 5) border_left_word(srow, drow, lane - 5);
-            if (right && lane >= 5 && lane - 5 < nright) border_right_word(srow, drow, rw0 + lane - 5, L.w);
-        }
-    }
 }
 
-// copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  16 lanes per plane row.  A border word
+// copyMakeBorder(BORDER_REFLECT_101) of every level (:1193, :1213).  Nothing on the extraction path reads the border: FAST, IC_Angle
+// and the stereo windows stay inside the level, and k_blur7 mirrors its own 3-px halo.  Only a caller that takes mvImagePyramid
+// out of the device sees it (the reference's level Mats are ROIs of bordered buffers, :1173-1177), so the host side launches
+// this kernel on demand -- batch extraction never writes those 200 KB per frame.  16 lanes per plane row.  A border word
 // (4 pixels) is a byte-reversed, funnel-shifted window of the level row: for the left strip pixels dx..dx+3
 // (dx < 0) mirror level pixels -dx-3..-dx, for the right strip they mirror 2(w-1)-dx-3..2(w-1)-dx.  The word
 // that straddles level and border keeps its level bytes.  Band rows (the 19 rows above / below the level)
@@ -303,7 +239,7 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
 #define ORBX_BORDER_ROWS 64
 __global__ void __launch_bounds__(256)
 k_pyr_border(const __grid_constant__ OrbxPlan plan, const OrbxWs ws) {
-    const int level = blockIdx.y + 1;                          // level 0's border comes from k_pyr_level0
+    const int level = blockIdx.y;
     const int frame = blockIdx.z;
     const OrbxLevel& L = plan.lv[level];
     const int lane = threadIdx.x;                              // 0..15
@@ -601,9 +537,12 @@ __device__ __forceinline__ void ft_word_flags(unsigned c, unsigned u, unsigned d
     }
 }
 
-// Flags of one aligned 8-byte pair (8 pixels) at 32-bit word index b of the tile, in the layout
-// {bit 0, 16, 1, 17, 2, 18, 3, 19} = pixels 0..7 (other bits are garbage: the caller masks with its valid-pixel word).
-__device__ __forceinline__ unsigned ft_pair_flags(const uint32_t* __restrict__ t32, int b, int tpw, unsigned KT) {
+// Flags of one aligned 8-byte pair (8 pixels) at 32-bit word index b of the tile: pixel k of the pair -> bit 8k+7 (k < 4),
+// bit 8(k-4)+3 (k >= 4).  The sign bits (15, 31) of the four flag words sit in their bytes 1 and 3: two PRMTs gather them as
+// the top bits of 4 + 4 bytes, one shift interleaves the second word, and the caller's valid-pixel mask (a subset of
+// 0x88888888) removes everything else.
+#define ORBX_FT_FULL 0x88888888u
+__device__ __forceinline__ unsigned ft_pair_flags(const uint32_t* __restrict__ t32, int b, int tpw, unsigned KT, unsigned valid) {
     const unsigned wl = t32[b - 1], wr = t32[b + 2];
     const uint2 wc = *reinterpret_cast<const uint2*>(t32 + b);
     const uint2 wu = *reinterpret_cast<const uint2*>(t32 + b - 3 * tpw);
@@ -611,25 +550,28 @@ __device__ __forceinline__ unsigned ft_pair_flags(const uint32_t* __restrict__ t
     unsigned z00, z01, z10, z11;
     ft_word_flags(wc.x, wu.x, wd.x, __funnelshift_r(wl, wc.x, 8), __funnelshift_r(wc.x, wc.y, 24), KT, z00, z01);
     ft_word_flags(wc.y, wu.y, wd.y, __funnelshift_r(wc.x, wc.y, 8), __funnelshift_r(wc.y, wr, 24), KT, z10, z11);
-    return (z00 >> 15) | (z01 >> 14) | (z10 >> 13) | (z11 >> 12);
+    const unsigned A = __byte_perm(z00, z01, 0x7531), B = __byte_perm(z10, z11, 0x7531) >> 4;
+    return ((A & 0x80808080u) | (B & 0x08080808u)) & valid;
 }
 
 // 8-bit pixel mask of a pair -> the flag layout above
 __device__ __forceinline__ unsigned ft_spread8(unsigned m) {
-    return (m & 1u) | ((m & 2u) << 15) | ((m & 4u) >> 1) | ((m & 8u) << 14) | ((m & 0x10u) >> 2) | ((m & 0x20u) << 13) | ((m & 0x40u) >> 3) |
-           ((m & 0x80u) << 12);
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s |= ((m >> k) & 1u) << (k < 4 ? 8 * k + 7 : 8 * (k - 4) + 3);
+    return s;
 }
 
 // Queue the flagged pixels of one pair; p0 = tile byte index of the pair's first pixel.
 __device__ __forceinline__ int ft_queue_pair(uint16_t* __restrict__ queue, int pos, unsigned mk, int p0) {
-    if (mk & 0x00000001u) queue[pos++] = (uint16_t)(p0 + 0);
-    if (mk & 0x00010000u) queue[pos++] = (uint16_t)(p0 + 1);
-    if (mk & 0x00000002u) queue[pos++] = (uint16_t)(p0 + 2);
-    if (mk & 0x00020000u) queue[pos++] = (uint16_t)(p0 + 3);
-    if (mk & 0x00000004u) queue[pos++] = (uint16_t)(p0 + 4);
-    if (mk & 0x00040000u) queue[pos++] = (uint16_t)(p0 + 5);
-    if (mk & 0x00000008u) queue[pos++] = (uint16_t)(p0 + 6);
-    if (mk & 0x00080000u) queue[pos++] = (uint16_t)(p0 + 7);
+    if (mk & 0x00000080u) queue[pos++] = (uint16_t)(p0 + 0);
+    if (mk & 0x00008000u) queue[pos++] = (uint16_t)(p0 + 1);
+    if (mk & 0x00800000u) queue[pos++] = (uint16_t)(p0 + 2);
+    if (mk & 0x80000000u) queue[pos++] = (uint16_t)(p0 + 3);
+    if (mk & 0x00000008u) queue[pos++] = (uint16_t)(p0 + 4);
+    if (mk & 0x00000800u) queue[pos++] = (uint16_t)(p0 + 5);
+    if (mk & 0x00080000u) queue[pos++] = (uint16_t)(p0 + 6);
+    if (mk & 0x08000000u) queue[pos++] = (uint16_t)(p0 + 7);
     return pos;
 }
 
@@ -651,6 +593,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     uint8_t* tile = smem_ft;
     uint8_t* score = smem_ft + map_bytes;
     uint16_t* queue = reinterpret_cast<uint16_t*>(smem_ft + 2 * map_bytes);
+    uint16_t* surv = queue + plan.ft_qcap;                          // NMS survivors (a strict 3x3 maximum: at most one pixel in four)
     const int th_rows = T.th, tw = T.tw;
     const int a16 = (ORBX_PADL + T.x0) & 15;
 
@@ -658,10 +601,9 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     {
         const uint8_t* g = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + T.y0) * L.pitch + (ORBX_PADL + T.x0 - a16);
         const int nvec = (a16 + tw + 15) >> 4;
-        const unsigned vmagic = 65536u / (unsigned)nvec + 1u;          // i / nvec for i < 2^11 (nvec <= 32)
         const int total = nvec * th_rows;
         for (int i = tid; i < total; i += ORBX_FT_THREADS) {
-            const int r = (int)(((unsigned)i * vmagic) >> 16);
+            const int r = (int)__umulhi((unsigned)i, T.vmagic);
             const int v = i - r * nvec;
             __pipeline_memcpy_async(tile + r * tp + 16 * v, g + (long long)r * L.pitch + 16 * v, 16);
         }
@@ -677,9 +619,6 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     const int nrows = th_rows - 6;
     const int ncells = T.ncells, wcell = T.wcell;
     const unsigned all_cells = (1u << ncells) - 1u;
-    int* counter = ws.cand_count + frame * plan.nlevels + T.level;
-    uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
-    const unsigned tpmagic = 0xffffffffu / (unsigned)tp + 1u;          // p / tp by __umulhi (p < 2^16; checked by the host for the plan's tp)
 
     unsigned empty = all_cells;                                        // cells still without a keypoint
     for (int phase = 0; phase < 2; ++phase) {
@@ -702,8 +641,8 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                         const int r = (int)__umulhi((unsigned)i, T.pmagic);
                         const int k = i - r * npairs;
                         const int b = (r + 3) * tpw + 2 * (pq0 + k);
-                        const unsigned valid = (k == 0 ? T.first_mask : 0x000f000fu) & (k == npairs - 1 ? T.last_mask : 0x000f000fu);
-                        mk[g] = ft_pair_flags(t32, b, tpw, KT) & valid;
+                        const unsigned valid = (k == 0 ? T.first_mask : ORBX_FT_FULL) & (k == npairs - 1 ? T.last_mask : ORBX_FT_FULL);
+                        mk[g] = ft_pair_flags(t32, b, tpw, KT, valid);
                         p0[g] = 4 * b;
                     }
                 }
@@ -744,7 +683,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                     if (8 * pq <= hi) {
                         const unsigned m8 = (0xffu << max(lo - 8 * pq, 0)) & (0xffu >> max(8 * pq + 7 - hi, 0)) & 0xffu;
                         const int b = (r + 3) * tpw + 2 * pq;
-                        mk = ft_pair_flags(t32, b, tpw, KT) & ft_spread8(m8);
+                        mk = ft_pair_flags(t32, b, tpw, KT, ft_spread8(m8));
                         p0 = 4 * b;
                     }
                 }
@@ -762,42 +701,41 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
             }
         }
         __syncthreads();
-        // ---- stage 2: exact corner measure of the queued pixels ----
+        // ---- stage 2: exact corner measure of the queued pixels; entries at or below the threshold are struck out ----
         const int qn = s_qn;
         for (int e = tid; e < qn; e += ORBX_FT_THREADS) {
             const int p = queue[e];
             const int best = fast_best(tile, p, tp);
             if (best > use_th) score[p] = (uint8_t)best;
+            else queue[e] = 0xffff;
         }
         __syncthreads();
-        // ---- dense strict 3x3 NMS over the score map; survivors listed in the (now free) queue ----
-        {
-            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(score);
-            const int w0 = (a16 + 3) >> 2, nw = ((a16 + tw - 4) >> 2) - w0 + 1;
-            const unsigned wmagic = 0xffffffffu / (unsigned)nw + 1u;
-            const int nitems = nw * nrows;
-            for (int i = tid; i < nitems; i += ORBX_FT_THREADS) {
-                const int r = (int)__umulhi((unsigned)i, wmagic);
-                const int w = w0 + (i - r * nw);
-                const int wi = (r + 3) * tpw + w;
-                unsigned wc = s32[wi];
-                if (wc == 0u) continue;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int s = (int)((wc >> (8 * k)) & 0xffu);
-                    if (s == 0) continue;
-                    const int p = 4 * wi + k;
-                    const int xi = 4 * w + k - a16 - 3;                      // interior column (>= 0: only interior pixels are scored)
-                    const int c = (int)__umulhi((unsigned)xi, T.cmagic);
-                    if (!((empty >> c) & 1u)) continue;                      // phase 1: cells that already have keypoints are done
-                    const int rem = xi - c * wcell;
-                    int nb = max((int)score[p - tp], (int)score[p + tp]);
-                    if (rem != 0) nb = max(nb, max((int)score[p - 1], max((int)score[p - tp - 1], (int)score[p + tp - 1])));
-                    if (rem != wcell - 1) nb = max(nb, max((int)score[p + 1], max((int)score[p - tp + 1], (int)score[p + tp + 1])));
-                    if (s > nb) {
-                        queue[atomicAdd(&s_ns, 1)] = (uint16_t)p;
-                        atomicOr(&s_flags, 1 << c);
-                    }
+        // ---- strict 3x3 non-max suppression inside the cell's detection interior (pixels at or below the threshold count as 0,
+        // like cv::FAST); survivors are appended to their own list, one shared-memory atomic per warp and round ----
+        for (int base = 0; base < qn; base += ORBX_FT_THREADS) {
+            const int e = base + tid;
+            const int p = e < qn ? queue[e] : 0xffff;
+            bool keep = false;
+            int c = 0;
+            if (p != 0xffff) {
+                const int s = score[p];
+                const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
+                const int xi = p - r * tp - a16 - 3;                         // interior column
+                c = (int)__umulhi((unsigned)xi, T.cmagic);
+                const int rem = xi - c * wcell;
+                int nb = max((int)score[p - tp], (int)score[p + tp]);
+                if (rem != 0) nb = max(nb, max((int)score[p - 1], max((int)score[p - tp - 1], (int)score[p + tp - 1])));
+                if (rem != wcell - 1) nb = max(nb, max((int)score[p + 1], max((int)score[p - tp + 1], (int)score[p + tp + 1])));
+                keep = s > nb;
+            }
+            const unsigned bal = __ballot_sync(ORBX_FULL_MASK, keep);
+            if (bal) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_ns, __popc(bal));
+                wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 0);
+                if (keep) {
+                    surv[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
+                    atomicOr(&s_flags, 1 << c);
                 }
             }
         }
@@ -807,18 +745,19 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         if (tid == 0) {
             int b0 = 0;
             if (ns > 0) {
-                b0 = atomicAdd(counter, ns);
+                b0 = atomicAdd(ws.cand_count + frame * plan.nlevels + T.level, ns);
                 if (b0 + ns > L.cand_cap) atomicOr(ws.flags, 1);
             }
             s_base = b0;
         }
         __syncthreads();
         const int slot0 = s_base;
+        uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
         for (int e = tid; e < ns; e += ORBX_FT_THREADS) {
             const int slot = slot0 + e;
             if (slot >= L.cand_cap) break;
-            const int p = queue[e];
-            const int r = (int)__umulhi((unsigned)p, tpmagic);
+            const int p = surv[e];
+            const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
             const int x = p - r * tp - a16;                                  // tile image column (>= 3)
             const int c = (int)__umulhi((unsigned)(x - 3), T.cmagic);
             const int xc = x - c * wcell;                                    // column inside the cell image
@@ -827,7 +766,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                                     (T.ordbase + ((uint32_t)c << ORBX_ORD_CELL_SHIFT)) | ((uint32_t)r << 7) | (uint32_t)xc);
         }
         empty = all_cells & ~(unsigned)s_flags;
-        __syncthreads();                                                     // s_flags / queue are rewritten by the next phase
+        __syncthreads();                                                     // s_flags / queue / surv are rewritten by the next phase
         if (tid == 0) { s_qn = 0; s_ns = 0; }
         __syncthreads();
     }
@@ -1166,17 +1105,37 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int tid = threadIdx.x;
     {
+        // BORDER_REFLECT_101 of the borderless clone the reference blurs (:1126-1127), without reading the plane's border (it may
+        // not have been written, see k_pyr_border): halo rows come from the mirrored level row, the 3 halo columns of the tiles
+        // on the left / right edge are mirrored in shared memory below.
         const int max_chunk = (L.pitch >> 4) - 1, c0 = (ORBX_PADL + x0 - 16) >> 4;
         for (int i = tid; i < SROWS * (SPB / 16); i += 256) {
             const int r = i / (SPB / 16), c = i - r * (SPB / 16);
-            const int pr = min(ORBX_EDGE + y0 + r - 3, L.plane_rows - 1);
+            const int lr = reflect101(min(y0 + r - 3, L.h + 2), L.h);
             __pipeline_memcpy_async(reinterpret_cast<uint8_t*>(s_src) + r * SPB + 16 * c,
-                                    plane + (long long)pr * L.pitch + 16 * min(c0 + c, max_chunk), 16);
+                                    plane + (long long)(ORBX_EDGE + lr) * L.pitch + 16 * min(c0 + c, max_chunk), 16);
         }
         __pipeline_commit();
         __pipeline_wait_prior(0);
     }
     __syncthreads();
+    {
+        // staged byte 16 + (x - x0) of a row holds level column x
+        const bool left = x0 == 0, right = L.w <= x0 + ORBX_BLUR_TW;
+        if (left || right) {
+            uint8_t* sb = reinterpret_cast<uint8_t*>(s_src);
+            if (tid < 2 * SROWS) {
+                const int r = tid >> 1, side = tid & 1;
+                uint8_t* row = sb + r * SPB + 16;
+                if (side == 0 && left) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
+                if (side == 1 && right) {
+                    const int e = L.w - x0;                              // first column past the level, 1 <= e <= 128
+                    row[e] = row[e - 2]; row[e + 1] = row[e - 3]; row[e + 2] = row[e - 4];
+                }
+            }
+            __syncthreads();
+        }
+    }
     // ---- horizontal: item = (row pair, 4-pixel group); output x reads staged bytes x+13 .. x+19 ----
     const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
     // partial tiles (right / bottom edge of a level): horizontal sums nobody reads are not computed

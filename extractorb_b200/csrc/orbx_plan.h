@@ -58,6 +58,8 @@ struct OrbxPlan {
     int ft_tp;             // k_fast_tiles: smem tile pitch (bytes, multiple of 16), rows, queue capacity (entries)
     int ft_trows;
     int ft_qcap;
+    int ft_scap;           // NMS survivor list capacity (entries)
+    unsigned ft_tpmagic;   // 2^32 / ft_tp + 1: tile byte index -> row (__umulhi)
     int lap0, lap1;
     int umax[ORBX_HALF_PATCH + 1];
     OrbxLevel lv[ORBX_MAX_LEVELS];
@@ -97,7 +99,8 @@ struct OrbxFastTile {           // 48 bytes, read as three uint4
     uint8_t pq0, npairs;        // first 8-byte pair holding an interior pixel, pairs per row
     uint16_t nitems;            // npairs * (th - 6)
     uint32_t first_mask, last_mask;   // interior-pixel flags of the first / last pair, in the flag layout of k_fast_tiles
-    uint32_t reserved[2];
+    uint32_t vmagic;            // 2^32 / (16-byte chunks per tile row) + 1: staging item -> row
+    uint32_t reserved;
 };
 static_assert(sizeof(OrbxFastTile) == 48, "OrbxFastTile is read as three uint4");
 

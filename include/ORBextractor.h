@@ -60,7 +60,8 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Level l is a w_l x h_l ROI at (19,19) of a bordered buffer, like the reference (:1173-1177).
+    // Level l is a w_l x h_l ROI at (19,19) of a bordered buffer, like the reference (:1173-1177).  The buffers belong to the
+    // extractor (one pinned block, refilled by every call that rebuilds the pyramid); clone() a level to keep it longer.
     std::vector<cv::Mat> mvImagePyramid;
     const std::vector<cv::Mat>& GetPyramid() const { return mvImagePyramid; }
 
@@ -106,6 +107,8 @@ private:
     OrbxHandle* mpHandle;
     int mnDevice;
     bool mbDownloadPyramid;
+    unsigned char* mpPyramidHost;      // pinned block holding the bordered planes of mvImagePyramid (one copy per call)
+    size_t mnPyramidHostBytes;
     std::string mLastError;
 };
 

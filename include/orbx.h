@@ -57,6 +57,8 @@ typedef struct OrbxParams {
 #define ORBX_FLAG_PROFILE 1 /* record CUDA-event time per stage (orbx_stage_times) */
 #define ORBX_FLAG_NO_GRAPH 2 /* never replay small launch groups as CUDA graphs */
 #define ORBX_FLAG_SINGLE_STREAM 4 /* do not overlap consecutive launch groups on two compute streams */
+#define ORBX_FLAG_COPY_ONLY 8 /* measurement aid: orbx_extract_batch moves the same bytes through the same staging slots, streams
+                                 and events but launches no kernel (outputs are unspecified): the copy bound of the host pipeline */
 
 /* Same 28-byte layout as cv::KeyPoint. */
 typedef struct OrbxKeyPoint {
@@ -115,6 +117,16 @@ ORBX_API int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem
                        OrbxKeyPoint* kps, uint8_t* desc, int cap_per_frame, int32_t* counts, int out_mem,
                        void* stream);
 
+/* The same call over several devices of one box from one process: handles[i] (each created on its own device) is driven by
+ * its own host thread through the pipeline above, and the threads pull launch groups from one shared cursor -- the reference's
+ * own concurrency pattern (two extractor instances on two host threads, src/Frame.cc:109-112) widened to n devices.  A device
+ * that is fed more slowly takes fewer groups, so all finish together.  images / kps / desc / counts are HOST buffers (pinned
+ * for full speed), laid out as for orbx_extract_batch; frames_per_handle (n_handles ints, may be NULL) receives how many
+ * frames each handle processed.  Results do not depend on which device processed a frame. */
+ORBX_API int orbx_extract_batch_multi(OrbxHandle* const* handles, int n_handles, const uint8_t* images, int n_frames, int width,
+                             int height, size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps,
+                             uint8_t* desc, int cap_per_frame, int32_t* counts, int32_t* frames_per_handle);
+
 /* Stage-wise entry points mirroring the reference's public methods (inc/ORBextractor.h:89-92), which the
  * demos call directly (src/orb_extractor/main_orb_extractor.cpp:44-46). */
 ORBX_API int orbx_compute_pyramid(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride);
@@ -130,6 +142,23 @@ ORBX_API int orbx_get_level_size(const OrbxHandle* h, int level, int* width, int
 /* mvImagePyramid[level] (inc/ORBextractor.h:85): with_border=0 copies the w x h level, 1 the
  * (w+38) x (h+38) plane including the 19-px reflect-101 border. */
 ORBX_API int orbx_get_pyramid_level(OrbxHandle* h, int frame, int level, uint8_t* dst, size_t dst_stride, int with_border);
+/* mvImagePyramid in one piece.  The library keeps a frame's bordered planes in one block of *frame_bytes bytes: level l starts
+ * at plane_offset[l], has level_h[l] + 2 * ORBX_PLANE_BORDER rows of pitch[l] bytes, and its level pixel (0, 0) sits at row
+ * ORBX_PLANE_BORDER, byte ORBX_PLANE_PADL of a row (the 19-px reflect-101 border lies around it, reference :1173-1177, :1193).
+ * Arrays take nlevels entries; any pointer may be NULL. */
+#define ORBX_PLANE_BORDER 19
+#define ORBX_PLANE_PADL 32
+ORBX_API int orbx_get_pyramid_layout(OrbxHandle* h, int width, int height, size_t* frame_bytes, size_t* plane_offset, int32_t* pitch,
+                            int32_t* level_w, int32_t* level_h);
+/* One copy of resident frame `frame`'s whole block into host_dst (capacity >= *frame_bytes; pinned memory for full speed). */
+ORBX_API int orbx_download_pyramid(OrbxHandle* h, int frame, uint8_t* host_dst, size_t capacity);
+/* Sink for the pyramids of every frame of the following orbx_extract* calls: frame f's block is copied to
+ * host_dst + f * frame_stride inside the call's own pipeline (the reference leaves mvImagePyramid on the host after every
+ * operator() call).  NULL switches it off (the default: keypoints and descriptors only). */
+ORBX_API int orbx_set_pyramid_output(OrbxHandle* h, uint8_t* host_dst, size_t frame_stride);
+/* Pinned (page-locked, portable) host memory for frame / result buffers; write_combined != 0 for buffers the CPU only writes. */
+ORBX_API void* orbx_host_alloc(size_t bytes, int write_combined);
+ORBX_API void orbx_host_free(void* p);
 /* allKeypoints[level] in level coordinates with angle set (== allLevelsKeypoints, ORBextractor.cc:1094). */
 ORBX_API int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* kps, int capacity, int* n_out);
 /* FAST candidates of the cell loop (ORBextractor.cc:855-860): x, y relative to (16,16), score, and the

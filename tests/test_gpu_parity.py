@@ -414,3 +414,23 @@ def test_fast_v1_v2_same_candidates(gpu, monkeypatch):
             for a, b in zip(out[0][0][l], out[1][0][l]):
                 assert np.array_equal(a, b), (w, h, cell, kind, l)
         assert kp_bytes_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+def test_extract_batch_multi_two_handles(gpu):
+    """orbx_extract_batch_multi: several handles (here two on the one device of the test box; one per GPU in production) pull
+    launch groups from a shared cursor.  Every frame is processed exactly once and the bytes equal the single-handle call,
+    whichever handle took the frame."""
+    frames = synth_batch(8, 160, 120, seed0=40)
+    frames = np.concatenate([frames, frames[:, ::-1].copy(), np.roll(frames, 17, 2), np.roll(frames, 9, 1)])[:27]
+    one = gpu.ORBextractor(400, 1.2, 3, 20, 7, max_batch=4)
+    rc, rk, rd = one.extract_batch_host(frames, (0, 100))
+    a = gpu.ORBextractor(400, 1.2, 3, 20, 7, max_batch=4)
+    b = gpu.ORBextractor(400, 1.2, 3, 20, 7, max_batch=4)
+    for handles in ([a], [a, b], [a, b, one]):
+        c, k, d, per = gpu.extract_batch_multi(handles, frames, (0, 100))
+        assert sum(per) == len(frames) and all(p >= 0 for p in per)
+        assert np.array_equal(c, rc)
+        for f in range(len(frames)):
+            m = c[f, 0]
+            assert k[f, :m].tobytes() == rk[f, :m].tobytes() and np.array_equal(d[f, :m], rd[f, :m]), f
+    one.close(); a.close(); b.close()
