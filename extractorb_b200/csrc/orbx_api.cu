@@ -466,6 +466,10 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
     ORBX_CUDA(cudaMalloc(&w.blur, (size_t)pe->blur_stride * frames));
     ORBX_CUDA(cudaMalloc(&w.cand, (size_t)pe->cand_stride * frames * sizeof(uint2)));
     ORBX_CUDA(cudaMalloc(&w.keynode, (size_t)pe->cand_stride * frames * sizeof(uint16_t)));
+    if (getenv("ORBX_POISON")) {   // test aid: stale workspace bytes (unwritten borders, padding) must never reach a result
+        ORBX_CUDA(cudaMemset(w.pyr, 0xA5, (size_t)pe->pyr_stride * frames));
+        ORBX_CUDA(cudaMemset(w.blur, 0x5A, (size_t)pe->blur_stride * frames));
+    }
     ORBX_CUDA(cudaMalloc(&w.kprec, (size_t)P.kp_total * frames * sizeof(OrbxKpRec)));
     ORBX_CUDA(cudaMalloc(&w.cand_count, (size_t)P.nlevels * frames * sizeof(int)));
     ORBX_CUDA(cudaMalloc(&w.level_count, (size_t)P.nlevels * frames * sizeof(int2)));

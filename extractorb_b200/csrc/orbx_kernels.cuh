@@ -1121,7 +1121,8 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
     __syncthreads();
     {
         // staged byte 16 + (x - x0) of a row holds level column x
-        const bool left = x0 == 0, right = L.w <= x0 + ORBX_BLUR_TW;
+        // right: the level ends inside this tile or inside its 3-column halo (a level of 257 columns: the tile [128, 256) reads 256..258)
+        const bool left = x0 == 0, right = L.w <= x0 + ORBX_BLUR_TW + 2;
         if (left || right) {
             uint8_t* sb = reinterpret_cast<uint8_t*>(s_src);
             if (tid < 2 * SROWS) {
@@ -1129,7 +1130,7 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
                 uint8_t* row = sb + r * SPB + 16;
                 if (side == 0 && left) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
                 if (side == 1 && right) {
-                    const int e = L.w - x0;                              // first column past the level, 1 <= e <= 128
+                    const int e = L.w - x0;                              // first column past the level, 1 <= e <= 130
                     row[e] = row[e - 2]; row[e + 1] = row[e - 3]; row[e + 2] = row[e - 4];
                 }
             }

@@ -434,3 +434,29 @@ def test_extract_batch_multi_two_handles(gpu):
             m = c[f, 0]
             assert k[f, :m].tobytes() == rk[f, :m].tobytes() and np.array_equal(d[f, :m], rd[f, :m]), f
     one.close(); a.close(); b.close()
+
+
+@pytest.mark.parametrize("w,h", [(128, 100), (129, 101), (130, 128), (131, 129), (255, 190), (256, 191), (257, 192), (258, 193), (259, 194),
+                                 (384, 130), (385, 131), (640, 480)])
+def test_batch_path_never_reads_the_border(gpu, oracle, monkeypatch, w, h):
+    """Launch groups of more than two frames skip the 19-px border (nothing on the path reads it; k_blur7 mirrors its own halo).
+    With the workspace poisoned at allocation (ORBX_POISON), blurred levels, keypoints and descriptors of a 3-frame group must
+    still equal the oracle -- level widths around the multiples of the blur tile (128) put the level's end inside a tile's
+    halo -- and planes taken out of the device afterwards must carry their border (written on demand)."""
+    monkeypatch.setenv("ORBX_POISON", "1")
+    frames = np.stack([synth_frame(3 * w + h + i, w, h) for i in range(3)])
+    nl = 2 if min(w, h) >= 120 else 1
+    ext = gpu.ORBextractor(600, 1.2, nl, 20, 7, max_batch=3)
+    counts, kps, desc = ext.extract_batch_host(frames, (0, 0))
+    o = oracle.OracleExtractor(600, 1.2, nl, 20, 7)
+    for f in range(3):
+        oret, okps, odesc = o.extract(frames[f], (0, 0))
+        n = counts[f, 0]
+        assert n == len(okps) and counts[f, 1] == oret
+        assert kp_bytes_equal(kps[f, :n], okps) and np.array_equal(desc[f, :n], odesc), f
+        for l in range(nl):
+            ob = o.level_blur(l)
+            if ob is not None:
+                assert np.array_equal(ext.blurred_level(l, frame=f), ob), (f, l)
+            assert np.array_equal(ext.pyramid_level(l, frame=f, with_border=True), o.level_plane(l)), (f, l)
+    ext.close()
