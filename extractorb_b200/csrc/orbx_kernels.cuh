@@ -562,24 +562,25 @@ __device__ __forceinline__ unsigned ft_spread8(unsigned m) {
     return s;
 }
 
-// Queue the flagged pixels of one pair; p0 = tile byte index of the pair's first pixel.
-__device__ __forceinline__ int ft_queue_pair(uint16_t* __restrict__ queue, int pos, unsigned mk, int p0) {
-    if (mk & 0x00000080u) queue[pos++] = (uint16_t)(p0 + 0);
-    if (mk & 0x00008000u) queue[pos++] = (uint16_t)(p0 + 1);
-    if (mk & 0x00800000u) queue[pos++] = (uint16_t)(p0 + 2);
-    if (mk & 0x80000000u) queue[pos++] = (uint16_t)(p0 + 3);
-    if (mk & 0x00000008u) queue[pos++] = (uint16_t)(p0 + 4);
-    if (mk & 0x00000800u) queue[pos++] = (uint16_t)(p0 + 5);
-    if (mk & 0x00080000u) queue[pos++] = (uint16_t)(p0 + 6);
-    if (mk & 0x08000000u) queue[pos++] = (uint16_t)(p0 + 7);
-    return pos;
+// Queue the flagged pixels of one pair; p0 = tile byte index of the pair's first pixel, qa = shared-memory byte address of the
+// next free queue slot (a running address: test, value, predicated store, predicated bump per pixel).
+__device__ __forceinline__ unsigned ft_queue_pair(unsigned qa, unsigned mk, int p0) {
+#define ORBX_FT_PUSH(bit, k)                                                                             \
+    if (mk & (bit)) {                                                                                    \
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(p0 + (k))) : "memory"); \
+        qa += 2;                                                                                         \
+    }
+    ORBX_FT_PUSH(0x00000080u, 0) ORBX_FT_PUSH(0x00008000u, 1) ORBX_FT_PUSH(0x00800000u, 2) ORBX_FT_PUSH(0x80000000u, 3)
+    ORBX_FT_PUSH(0x00000008u, 4) ORBX_FT_PUSH(0x00000800u, 5) ORBX_FT_PUSH(0x00080000u, 6) ORBX_FT_PUSH(0x08000000u, 7)
+#undef ORBX_FT_PUSH
+    return qa;
 }
 
 __global__ void __launch_bounds__(ORBX_FT_THREADS)
 k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int tile_base) {
     extern __shared__ __align__(16) uint8_t smem_ft[];
-    __shared__ int s_qn, s_ns, s_flags, s_base;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ int s_qn, s_flags;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int frame = blockIdx.y;
     OrbxFastTile T;
     {
@@ -593,7 +594,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     uint8_t* tile = smem_ft;
     uint8_t* score = smem_ft + map_bytes;
     uint16_t* queue = reinterpret_cast<uint16_t*>(smem_ft + 2 * map_bytes);
-    uint16_t* surv = queue + plan.ft_qcap;                          // NMS survivors (a strict 3x3 maximum: at most one pixel in four)
+    const unsigned queue_sa = (unsigned)__cvta_generic_to_shared(queue);
     const int th_rows = T.th, tw = T.tw;
     const int a16 = (ORBX_PADL + T.x0) & 15;
 
@@ -610,7 +611,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         __pipeline_commit();
         const int nz = (th_rows * tp) >> 4;
         for (int i = tid; i < nz; i += ORBX_FT_THREADS) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { s_qn = 0; s_ns = 0; s_flags = 0; }
+        if (tid == 0) { s_qn = 0; s_flags = 0; }
         __pipeline_wait_prior(0);
     }
     __syncthreads();
@@ -619,6 +620,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     const int nrows = th_rows - 6;
     const int ncells = T.ncells, wcell = T.wcell;
     const unsigned all_cells = (1u << ncells) - 1u;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     unsigned empty = all_cells;                                        // cells still without a keypoint
     for (int phase = 0; phase < 2; ++phase) {
@@ -656,9 +658,9 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                 int wbase = 0;
                 if (lane == 31 && inc > 0) wbase = atomicAdd(&s_qn, inc);
                 wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 31);
-                int pos = wbase + inc - cnt;
-                pos = ft_queue_pair(queue, pos, mk[0], p0[0]);
-                ft_queue_pair(queue, pos, mk[1], p0[1]);
+                unsigned qa = queue_sa + 2u * (unsigned)(wbase + inc - cnt);
+                qa = ft_queue_pair(qa, mk[0], p0[0]);
+                ft_queue_pair(qa, mk[1], p0[1]);
             }
         } else {
             // only the cells that came out empty: items = (empty cell, row, pair of the cell's column span)
@@ -697,78 +699,91 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                 int wbase = 0;
                 if (lane == 31 && inc > 0) wbase = atomicAdd(&s_qn, inc);
                 wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 31);
-                ft_queue_pair(queue, wbase + inc - cnt, mk, p0);
+                ft_queue_pair(queue_sa + 2u * (unsigned)(wbase + inc - cnt), mk, p0);
             }
         }
         __syncthreads();
-        // ---- stage 2: exact corner measure of the queued pixels; entries at or below the threshold are struck out ----
+        // From here on every warp owns one contiguous chunk of the queue (whole rounds of 32 slots) and compacts it in place:
+        // the pixels that pass the exact measure move to the front of the chunk, then the NMS survivors do.  A round writes only
+        // slots it (or an earlier round) has already read, so no second buffer and no block-wide counters are needed, and the
+        // lanes of the next pass are dense again.
         const int qn = s_qn;
-        for (int e = tid; e < qn; e += ORBX_FT_THREADS) {
-            const int p = queue[e];
-            const int best = fast_best(tile, p, tp);
-            if (best > use_th) score[p] = (uint8_t)best;
-            else queue[e] = 0xffff;
+        const int chunk = ((qn + ORBX_FT_THREADS - 1) >> 8) << 5;
+        const int cbeg = wid * chunk, cend = min(cbeg + chunk, qn);
+        // ---- stage 2: exact corner measure of the queued pixels ----
+        int na = 0;
+        for (int e0 = cbeg; e0 < cend; e0 += 32) {
+            const int e = e0 + lane;
+            int p = 0;
+            bool alive = false;
+            if (e < cend) {
+                p = queue[e];
+                const int best = fast_best(tile, p, tp);
+                alive = best > use_th;
+                if (alive) score[p] = (uint8_t)best;
+            }
+            const unsigned bal = __ballot_sync(ORBX_FULL_MASK, alive);
+            if (alive) queue[cbeg + na + __popc(bal & lt_mask)] = (uint16_t)p;
+            na += __popc(bal);
         }
-        __syncthreads();
+        __syncthreads();                                                    // the score map is complete
         // ---- strict 3x3 non-max suppression inside the cell's detection interior (pixels at or below the threshold count as 0,
-        // like cv::FAST); survivors are appended to their own list, one shared-memory atomic per warp and round ----
-        for (int base = 0; base < qn; base += ORBX_FT_THREADS) {
-            const int e = base + tid;
-            const int p = e < qn ? queue[e] : 0xffff;
+        // like cv::FAST; the neighbours across a cell boundary column do not count) ----
+        int nsv = 0;
+        unsigned cflags = 0u;
+        for (int i0 = 0; i0 < na; i0 += 32) {
+            const int i = i0 + lane;
+            int p = 0;
             bool keep = false;
-            int c = 0;
-            if (p != 0xffff) {
+            if (i < na) {
+                p = queue[cbeg + i];
                 const int s = score[p];
                 const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
                 const int xi = p - r * tp - a16 - 3;                         // interior column
-                c = (int)__umulhi((unsigned)xi, T.cmagic);
+                const int c = (int)__umulhi((unsigned)xi, T.cmagic);
                 const int rem = xi - c * wcell;
                 int nb = max((int)score[p - tp], (int)score[p + tp]);
                 if (rem != 0) nb = max(nb, max((int)score[p - 1], max((int)score[p - tp - 1], (int)score[p + tp - 1])));
                 if (rem != wcell - 1) nb = max(nb, max((int)score[p + 1], max((int)score[p - tp + 1], (int)score[p + tp + 1])));
                 keep = s > nb;
+                if (keep) cflags |= 1u << c;
             }
             const unsigned bal = __ballot_sync(ORBX_FULL_MASK, keep);
-            if (bal) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_ns, __popc(bal));
-                wbase = __shfl_sync(ORBX_FULL_MASK, wbase, 0);
-                if (keep) {
-                    surv[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
-                    atomicOr(&s_flags, 1 << c);
-                }
+            if (keep) queue[cbeg + nsv + __popc(bal & lt_mask)] = (uint16_t)p;
+            nsv += __popc(bal);
+        }
+        cflags = __reduce_or_sync(ORBX_FULL_MASK, cflags);
+        if (lane == 0 && cflags) atomicOr(&s_flags, (int)cflags);
+        // ---- emission: one atomic per warp reserves the slots; entries carry the emission-order key (:855-860) ----
+        if (nsv > 0) {
+            int slot0 = 0;
+            if (lane == 0) {
+                slot0 = atomicAdd(ws.cand_count + frame * plan.nlevels + T.level, nsv);
+                if (slot0 + nsv > L.cand_cap) atomicOr(ws.flags, 1);
+            }
+            slot0 = __shfl_sync(ORBX_FULL_MASK, slot0, 0);
+            __syncwarp();
+            uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
+            for (int i = lane; i < nsv; i += 32) {
+                const int slot = slot0 + i;
+                if (slot >= L.cand_cap) break;
+                const int p = queue[cbeg + i];
+                const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
+                const int x = p - r * tp - a16;                              // tile image column (>= 3)
+                const int c = (int)__umulhi((unsigned)(x - 3), T.cmagic);
+                const int xc = x - c * wcell;                                // column inside the cell image
+                const uint32_t resp = (uint32_t)score[p] - 1u;
+                cand[slot] = make_uint2((uint32_t)(x + T.xoff) | ((uint32_t)(r + T.yoff) << ORBX_COORD_BITS) | (resp << 24),
+                                        (T.ordbase + ((uint32_t)c << ORBX_ORD_CELL_SHIFT)) | ((uint32_t)r << 7) | (uint32_t)xc);
             }
         }
-        __syncthreads();
-        // ---- emission: one atomic per tile reserves the slots; entries carry the emission-order key (:855-860) ----
-        const int ns = s_ns;
-        if (tid == 0) {
-            int b0 = 0;
-            if (ns > 0) {
-                b0 = atomicAdd(ws.cand_count + frame * plan.nlevels + T.level, ns);
-                if (b0 + ns > L.cand_cap) atomicOr(ws.flags, 1);
-            }
-            s_base = b0;
-        }
-        __syncthreads();
-        const int slot0 = s_base;
-        uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
-        for (int e = tid; e < ns; e += ORBX_FT_THREADS) {
-            const int slot = slot0 + e;
-            if (slot >= L.cand_cap) break;
-            const int p = surv[e];
-            const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
-            const int x = p - r * tp - a16;                                  // tile image column (>= 3)
-            const int c = (int)__umulhi((unsigned)(x - 3), T.cmagic);
-            const int xc = x - c * wcell;                                    // column inside the cell image
-            const uint32_t resp = (uint32_t)score[p] - 1u;
-            cand[slot] = make_uint2((uint32_t)(x + T.xoff) | ((uint32_t)(r + T.yoff) << ORBX_COORD_BITS) | (resp << 24),
-                                    (T.ordbase + ((uint32_t)c << ORBX_ORD_CELL_SHIFT)) | ((uint32_t)r << 7) | (uint32_t)xc);
-        }
+        __syncthreads();                                                     // every warp has reported its cells
         empty = all_cells & ~(unsigned)s_flags;
-        __syncthreads();                                                     // s_flags / queue / surv are rewritten by the next phase
-        if (tid == 0) { s_qn = 0; s_ns = 0; }
-        __syncthreads();
+        if (phase == 0 && plan.min_th < plan.ini_th && empty != 0u) {
+            __syncthreads();                                                 // everyone has read s_qn / s_flags
+            if (tid == 0) s_qn = 0;
+            __syncthreads();
+        }
     }
 }
 
