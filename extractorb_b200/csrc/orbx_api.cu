@@ -3,6 +3,7 @@
 //
 // Reference being replaced: ORB_SLAM3::ORBextractor (/root/reference/src/orb_extractor/ORBextractor.cc,
 // twin ORBExtractor.cpp).  Line citations below refer to ORBextractor.cc.
+#include <cuda.h>               // CUtensorMap types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a pointer test when no profiler is attached
 
@@ -84,6 +85,7 @@ struct OrbxHandle {
     int cand_per_cell = 64;
     int n_slots = 4;               // staging slots of the host-buffer pipeline (ORBX_SLOTS=2..4)
     bool ramp = true;              // ramp the launch-group size of host-buffer calls up / down (ORBX_RAMP=0 disables)
+    bool fast_tma = true;          // ORBX_FAST_TMA=0: stage the FAST tiles with cp.async instead of one TMA bulk tensor copy
     bool fast_v1 = false;          // ORBX_FAST_V1=1: the round-1 warp-per-cell FAST kernel (A/B measurements only)
     // plans keyed by image size
     std::map<std::pair<int, int>, PlanEntry*> plans;
@@ -445,7 +447,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
 }
 
 void free_ws_set(OrbxWs& w, bool own_flags) {
-    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode);
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps));
     cudaFree(w.kprec); cudaFree(w.cand_count); cudaFree(w.level_count);
     if (own_flags) cudaFree(w.flags);
     memset(&w, 0, sizeof(w));
@@ -458,6 +460,40 @@ void free_workspace(OrbxHandle* h) {
     free_ws_set(h->ws2, false);
     free_ws_set(h->ws, true);
     h->ws_plan = nullptr; h->ws_frames = 0; h->ws2_frames = 0; h->resident_frames = 0; h->cur = nullptr; h->res_set = 0;
+}
+
+// One 3-D tensor map per level over a workspace's pyramid block: (byte column, plane row, frame) with strides (pitch, pyr_stride),
+// box = ft_tp x ft_trows x 1 -- the FAST tile image of k_fast_tiles<true>.  Returns false when TMA cannot describe the plan (box
+// wider than 256 bytes, e.g. cell_size 60) or the driver entry point is missing: the cp.async instance is used instead.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool build_fast_tmaps(PlanEntry* pe, uint8_t* pyr, int frames, std::vector<CUtensorMap>& out) {
+    const OrbxPlan& P = pe->plan;
+    if (P.ft_tp > 256 || P.ft_trows > 256 || P.ntiles_total == 0) return false;
+    static PFN_encodeTiled encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = (PFN_encodeTiled)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    out.resize((size_t)P.nlevels);
+    for (int l = 0; l < P.nlevels; ++l) {
+        const OrbxLevel& V = P.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)V.pitch, (cuuint64_t)V.plane_rows, (cuuint64_t)frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)V.pitch, (cuuint64_t)pe->pyr_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)P.ft_tp, (cuuint32_t)P.ft_trows, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (encode(&out[(size_t)l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr + V.plane_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
 }
 
 int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* shared_flags) {
@@ -478,6 +514,16 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
     } else {
         ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
         ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
+    }
+    w.tmaps = nullptr;
+    if (h->fast_tma) {
+        std::vector<CUtensorMap> maps;
+        if (build_fast_tmaps(pe, w.pyr, frames, maps)) {
+            uint8_t* d = nullptr;
+            ORBX_CUDA(cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)));
+            ORBX_CUDA(cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+            w.tmaps = d;
+        }
     }
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
@@ -581,8 +627,10 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         if (h->fast_v1)
             k_fast_cells<<<dim3((V.ncells + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, sl>>>(P, ws, V.cell_off,
                                                                                                                               V.cell_off + V.ncells);
+        else if (V.ntiles > 0 && ws.tmaps)
+            k_fast_tiles<true><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         else if (V.ntiles > 0)
-            k_fast_tiles<<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
+            k_fast_tiles<false><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         k_octree<ORBX_QT_THREADS_BIG><<<dim3(1, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
         launches += 2;
         ORBX_CUDA(cudaEventRecord(h->ev_lvl_done[l], sl));
@@ -656,8 +704,10 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
         if (h->fast_v1)
             k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, 0, P.ncells_total);
+        else if (P.ntiles_total > 0 && ws.tmaps)
+            k_fast_tiles<true><<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
         else if (P.ntiles_total > 0)
-            k_fast_tiles<<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
+            k_fast_tiles<false><<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[2], st));
         nvtx_stage("orbx:octree");
@@ -784,7 +834,8 @@ int set_kernel_attrs_device(OrbxHandle* h) {
     int optin = 0;
     ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     ORBX_CUDA(raise_smem_limit(k_fast_cells, optin));
-    ORBX_CUDA(raise_smem_limit(k_fast_tiles, optin));
+    ORBX_CUDA(raise_smem_limit(k_fast_tiles<true>, optin));
+    ORBX_CUDA(raise_smem_limit(k_fast_tiles<false>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_LAT>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_BIG>, optin));
@@ -874,6 +925,7 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     h->cand_per_cell = prm->cand_per_cell > 0 ? prm->cand_per_cell : 64;
     h->device = device;
     if (const char* e1 = getenv("ORBX_FAST_V1")) h->fast_v1 = atoi(e1) != 0;
+    if (const char* e4 = getenv("ORBX_FAST_TMA")) h->fast_tma = atoi(e4) != 0;
     if (const char* e2 = getenv("ORBX_SLOTS")) h->n_slots = std::min(4, std::max(2, atoi(e2)));
     if (const char* e3 = getenv("ORBX_RAMP")) h->ramp = atoi(e3) != 0;
     build_ctor_tables(h);

@@ -576,10 +576,34 @@ __device__ __forceinline__ unsigned ft_queue_pair(unsigned qa, unsigned mk, int 
     return qa;
 }
 
+// TMA + mbarrier helpers (sm_90+ PTX; SASS: UTMALDG / SYNCS).  One thread arms the barrier with the byte count of the box and
+// issues the bulk tensor copy; the copy engine lands the box in shared memory and completes the barrier's transaction count.
+__device__ __forceinline__ void orbx_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void orbx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void orbx_tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ bool orbx_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// TMA: the tile image arrives as ONE bulk tensor copy (box = ft_tp bytes x ft_trows rows of the level's plane, described by
+// ws.tmaps[level]; columns / rows past the plane are zero-filled) instead of ~570 16-byte cp.async with their index arithmetic.
+template <bool TMA>
 __global__ void __launch_bounds__(ORBX_FT_THREADS)
 k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int tile_base) {
-    extern __shared__ __align__(16) uint8_t smem_ft[];
+    extern __shared__ __align__(128) uint8_t smem_ft[];
     __shared__ int s_qn, s_flags;
+    __shared__ __align__(8) unsigned long long s_bar;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int frame = blockIdx.y;
     OrbxFastTile T;
@@ -599,7 +623,22 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     const int a16 = (ORBX_PADL + T.x0) & 15;
 
     // ---- stage the tile image: whole 16-byte chunks of the plane rows (64-byte aligned), score map cleared meanwhile ----
-    {
+    if (TMA) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (tid == 0) orbx_mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            orbx_mbar_expect_tx(bar, (uint32_t)map_bytes);
+            orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(tile), ws.tmaps + 128 * T.level, bar, ORBX_PADL + T.x0 - a16, ORBX_EDGE + T.y0, frame);
+        }
+        const int nz = (th_rows * tp) >> 4;
+        for (int i = tid; i < nz; i += ORBX_FT_THREADS) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { s_qn = 0; s_flags = 0; }
+        unsigned spins = 0;
+        while (!orbx_mbar_try_wait(bar, 0)) {
+            if (++spins > (1u << 18)) __trap();                     // a copy that never lands must fail loudly, not hang the device
+        }
+    } else {
         const uint8_t* g = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + T.y0) * L.pitch + (ORBX_PADL + T.x0 - a16);
         const int nvec = (a16 + tw + 15) >> 4;
         const int total = nvec * th_rows;

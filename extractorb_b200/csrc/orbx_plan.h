@@ -127,6 +127,7 @@ struct OrbxWs {
     const int2* ytab;
     const OrbxCell* cells;
     const OrbxFastTile* tiles;
+    const uint8_t* tmaps;     // one 128-byte CUtensorMap per level over this workspace's planes (k_fast_tiles<true>), or NULL
     const float* pattern_f;   // rBRIEF tests as floats, layout [bit k][descriptor byte][x0, y0, x1, y1]
     const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
     const uint32_t* blur_tiles; // blur tile table: level | tile_x << 8 | tile_y << 20
