@@ -87,6 +87,16 @@ def load_library():
     L.orbx_get_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, sz]
     L.orbx_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]
+    L.orbx_stereo_match_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]
+    L.orbx_search_for_initialization_mem.argtypes = [vp, C.POINTER(FrameCalib), vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, C.c_float, i32,
+                                                     vp, C.POINTER(i32), i32]
+    L.orbx_get_pyramid_layout.argtypes = [vp, i32, i32, C.POINTER(sz), vp, vp, vp, vp]
+    L.orbx_download_pyramid.argtypes = [vp, i32, vp, sz]
+    L.orbx_set_pyramid_output.argtypes = [vp, vp, sz]
+    L.orbx_host_alloc.restype = vp
+    L.orbx_host_alloc.argtypes = [sz, i32]
+    L.orbx_host_free.restype = None
+    L.orbx_host_free.argtypes = [vp]
     L.orbx_frame_image_bounds.argtypes = [vp, C.POINTER(FrameCalib), i32, i32]
     L.orbx_frame_undistort_grid.argtypes = [vp, C.POINTER(FrameCalib), vp, i32, vp, vp, vp, C.POINTER(i32)]
     L.orbx_extract_frame.argtypes = [vp, vp, i32, i32, sz, i32, i32, C.POINTER(FrameCalib), vp, vp, i32, C.POINTER(i32), C.POINTER(i32), vp, vp, vp,
@@ -269,6 +279,27 @@ class ORBextractor:
         order = np.argsort(od[:n.value], kind="stable")
         return xs[:n.value][order], ys[:n.value][order], sc[:n.value][order]
 
+    def pyramid_layout(self, width, height):
+        """-> (frame_bytes, plane_offset[l], pitch[l], level_w[l], level_h[l]) of the bordered pyramid block (orbx_get_pyramid_layout)."""
+        fb = C.c_size_t(0)
+        off = (C.c_size_t * self.nlevels)()
+        pitch, lw, lh = ((C.c_int32 * self.nlevels)() for _ in range(3))
+        self._check(self._L.orbx_get_pyramid_layout(self._h, width, height, C.byref(fb), C.cast(off, C.c_void_p), C.cast(pitch, C.c_void_p),
+                                                    C.cast(lw, C.c_void_p), C.cast(lh, C.c_void_p)))
+        return fb.value, list(off), list(pitch), list(lw), list(lh)
+
+    def set_pyramid_output(self, host_ptr, frame_stride):
+        """Sink for every frame's bordered pyramid block in the following extract calls (None switches it off)."""
+        self._check(self._L.orbx_set_pyramid_output(self._h, host_ptr, frame_stride))
+
+    def download_pyramid(self, frame=0):
+        """The whole bordered block of resident frame `frame` in one copy -> uint8 array of frame_bytes."""
+        w, h = self.level_size(0)
+        fb = self.pyramid_layout(w, h)[0]
+        out = np.empty(fb, np.uint8)
+        self._check(self._L.orbx_download_pyramid(self._h, frame, out.ctypes.data, fb))
+        return out
+
     def stage_times(self):
         """-> (dict stage -> ms since last call, kernel launches since last call); needs profile=True."""
         ms = np.zeros(len(STAGE_NAMES), np.float32)
@@ -324,6 +355,22 @@ def stereo_match(left, right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
     left._check(left._L.orbx_stereo_match(left._h, right._h, keys_l.ctypes.data, desc_l.ctypes.data, len(keys_l), keys_r.ctypes.data,
                                           desc_r.ctypes.data, len(keys_r), float(mb), float(mbf), u.ctypes.data, d.ctypes.data, C.byref(n)))
     return u, d, n.value
+
+
+def stereo_match_batch_raw(left, right, n_pairs, kps_l, desc_l, counts_l, kps_r, desc_r, counts_r, cap_per_frame, mb, mbf, u_right, depth,
+                           n_matched, stream=None):
+    """orbx_stereo_match_batch on raw DEVICE pointers: all stereo pairs of the launch group both extractors hold resident."""
+    left._check(left._L.orbx_stereo_match_batch(left._h, right._h, n_pairs, kps_l, desc_l, counts_l, kps_r, desc_r, counts_r, cap_per_frame,
+                                                float(mb), float(mbf), u_right, depth, n_matched, stream))
+
+
+def search_for_initialization_raw(ext, calib, k1, d1, n1, k2, d2, n2, cell_start2, cell_items2, prev, window, nn_ratio, check_orientation,
+                                  matches12, mem):
+    """orbx_search_for_initialization_mem on raw pointers in `mem` memory -> nmatches."""
+    n = C.c_int(0)
+    ext._check(ext._L.orbx_search_for_initialization_mem(ext._h, C.byref(calib), k1, d1, n1, k2, d2, n2, cell_start2, cell_items2, prev, int(window),
+                                                         float(nn_ratio), 1 if check_orientation else 0, matches12, C.byref(n), mem))
+    return n.value
 
 
 # ---- the rows after the extractor in a Frame constructor / monocular initialisation (SURVEY.md 8(f) ranks 3, 2) ----

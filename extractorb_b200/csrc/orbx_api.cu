@@ -1474,6 +1474,7 @@ int orbx_stereo_match(OrbxHandle* h, OrbxHandle* right, const OrbxKeyPoint* keys
     OrbxStereoArgs a;
     a.kl = (const OrbxKeyPoint*)(b + o_kl); a.dl = (const uint32_t*)(b + o_dl); a.nl = n_l;
     a.kr = (const OrbxKeyPoint*)(b + o_kr); a.dr = (const uint32_t*)(b + o_dr); a.nr = n_r;
+    a.kp_stride = 0; a.pyr_stride = 0; a.counts_l = nullptr; a.counts_r = nullptr; a.cap = 0;
     a.pyr_l = res_ws(h).pyr; a.pyr_r = res_ws(right).pyr;     // frame 0 of each handle's resident group
     a.mbf = mbf; a.min_d = 0.f; a.max_d = mbf / mb;           // minZ = mb, maxD = mbf / minZ (:844-846)
     a.th_mul = 1.5f * 1.4f;
@@ -1488,6 +1489,37 @@ int orbx_stereo_match(OrbxHandle* h, OrbxHandle* right, const OrbxKeyPoint* keys
     ORBX_CUDA(cudaMemcpyAsync(&nm, b + o_n, 4, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     if (n_matched) *n_matched = nm;
+    return ORBX_OK;
+}
+
+// The same row for every stereo pair of the launch group the two handles hold resident, inputs and outputs on the device:
+// what orbx_extract_batch(..., ORBX_MEM_DEVICE) wrote goes straight into the matcher, nothing is downloaded and re-uploaded.
+int orbx_stereo_match_batch(OrbxHandle* h, OrbxHandle* right, int n_pairs, const OrbxKeyPoint* kps_l, const uint8_t* desc_l,
+                            const int32_t* counts_l, const OrbxKeyPoint* kps_r, const uint8_t* desc_r, const int32_t* counts_r,
+                            int cap_per_frame, float mb, float mbf, float* u_right, float* depth, int32_t* n_matched, void* stream) {
+    if (!h || !right) return ORBX_ERR_BAD_ARGUMENT;
+    if (n_pairs < 1 || cap_per_frame < 1 || cap_per_frame >= 65535 || !kps_l || !desc_l || !counts_l || !kps_r || !desc_r || !counts_r ||
+        !u_right || !depth || !n_matched || !(mb > 0.f))
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad stereo arguments");
+    if (!h->cur || !right->cur || h->resident_frames < n_pairs || right->resident_frames < n_pairs)
+        return fail(h, ORBX_ERR_NO_FRAME, "both extractors must hold the pairs' pyramids resident (one launch group)");
+    if (h->device != right->device || h->cur->plan.width != right->cur->plan.width || h->cur->plan.height != right->cur->plan.height ||
+        h->cur->plan.nlevels != right->cur->plan.nlevels)
+        return fail(h, ORBX_ERR_BAD_ARGUMENT, "left and right extractors must share device, image size and level count");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, (size_t)n_pairs * cap_per_frame * 4 + 256, false);
+    if (rc != ORBX_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    OrbxStereoArgs a;
+    a.kl = kps_l; a.dl = (const uint32_t*)desc_l; a.nl = 0; a.kr = kps_r; a.dr = (const uint32_t*)desc_r; a.nr = 0;
+    a.kp_stride = cap_per_frame; a.pyr_stride = h->cur->pyr_stride; a.counts_l = counts_l; a.counts_r = counts_r; a.cap = cap_per_frame;
+    a.pyr_l = res_ws(h).pyr; a.pyr_r = res_ws(right).pyr;
+    a.mbf = mbf; a.min_d = 0.f; a.max_d = mbf / mb; a.th_mul = 1.5f * 1.4f;
+    a.u_right = u_right; a.depth = depth; a.sad = (int*)h->d_stereo; a.n_matched = n_matched;
+    k_stereo_match<<<dim3((cap_per_frame + 7) / 8, n_pairs), 256, 0, st>>>(h->cur->plan, a);
+    k_stereo_filter<<<n_pairs, 256, 0, st>>>(a);
+    h->total_launches += 2; h->stage_launches += 2;
+    ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
 
@@ -1602,47 +1634,56 @@ int orbx_extract_frame(OrbxHandle* h, const uint8_t* image, int width, int heigh
     return ORBX_OK;
 }
 
-int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1, const uint8_t* desc1, int n1,
-                                   const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2, const int32_t* cell_start2,
-                                   const int32_t* cell_items2, float* prev_matched, int window_size, float nn_ratio,
-                                   int check_orientation, int32_t* matches12, int* n_matches) {
+int orbx_search_for_initialization_mem(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1, const uint8_t* desc1, int n1,
+                                       const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2, const int32_t* cell_start2,
+                                       const int32_t* cell_items2, float* prev_matched, int window_size, float nn_ratio,
+                                       int check_orientation, int32_t* matches12, int* n_matches, int mem) {
     if (!h) return ORBX_ERR_BAD_ARGUMENT;
     if (n_matches) *n_matches = 0;
-    if (!calib_ok(calib, true) || n1 < 0 || n2 < 0 || n2 > 32768 || !cell_start2 ||
+    if (!calib_ok(calib, true) || n1 < 0 || n2 < 0 || n2 > 32768 || !cell_start2 || (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) ||
         (n1 > 0 && (!keys_un1 || !desc1 || !prev_matched || !matches12)) || (n2 > 0 && (!keys_un2 || !desc2 || !cell_items2)))
         return fail(h, ORBX_ERR_BAD_ARGUMENT, "bad SearchForInitialization arguments");
     if (n1 == 0) return ORBX_OK;
-    const int n_items = cell_start2[ORBX_GRID_CELLS];
-    if (n_items < 0 || n_items > n2) return fail(h, ORBX_ERR_BAD_ARGUMENT, "grid does not belong to frame 2");
+    const bool dev = mem == ORBX_MEM_DEVICE;
+    int n_items = 0;
+    if (!dev) {
+        n_items = cell_start2[ORBX_GRID_CELLS];
+        if (n_items < 0 || n_items > n2) return fail(h, ORBX_ERR_BAD_ARGUMENT, "grid does not belong to frame 2");
+    }
     ORBX_CUDA(cudaSetDevice(h->device));
     const int m2 = std::max(n2, 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (size_t)align_up((long long)bytes, 256); return at; };
-    const size_t o_k1 = take((size_t)n1 * sizeof(OrbxKeyPoint)), o_d1 = take((size_t)n1 * 32), o_k2 = take((size_t)m2 * sizeof(OrbxKeyPoint));
-    const size_t o_d2 = take((size_t)m2 * 32), o_cs = take((ORBX_GRID_CELLS + 1) * 4), o_ci = take((size_t)m2 * 4), o_pv = take((size_t)n1 * 8);
-    const size_t o_sk = take((size_t)n1 * 32), o_si = take((size_t)n1 * 32), o_sc = take((size_t)n1 * 4), o_m = take((size_t)n1 * 4);
+    // device-resident inputs are used where they lie; only the kernels' scratch is allocated
+    const size_t o_k1 = dev ? 0 : take((size_t)n1 * sizeof(OrbxKeyPoint)), o_d1 = dev ? 0 : take((size_t)n1 * 32);
+    const size_t o_k2 = dev ? 0 : take((size_t)m2 * sizeof(OrbxKeyPoint)), o_d2 = dev ? 0 : take((size_t)m2 * 32);
+    const size_t o_cs = dev ? 0 : take((ORBX_GRID_CELLS + 1) * 4), o_ci = dev ? 0 : take((size_t)m2 * 4), o_pv = dev ? 0 : take((size_t)n1 * 8);
+    const size_t o_m = dev ? 0 : take((size_t)n1 * 4);
+    const size_t o_sk = take((size_t)n1 * 32), o_si = take((size_t)n1 * 32), o_sc = take((size_t)n1 * 4);
     const size_t o_p = take((size_t)n1 * 4), o_al = take((size_t)n1 * 4), o_n = take(8);
     int rc = ensure_bytes(h, (void**)&h->d_stereo, &h->d_stereo_bytes, o, false);
     if (rc != ORBX_OK) return rc;
     uint8_t* b = h->d_stereo;
     cudaStream_t st = h->stream;
-    ORBX_CUDA(cudaMemcpyAsync(b + o_k1, keys_un1, (size_t)n1 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
-    ORBX_CUDA(cudaMemcpyAsync(b + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
-    if (n2 > 0) {
-        ORBX_CUDA(cudaMemcpyAsync(b + o_k2, keys_un2, (size_t)n2 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
-        ORBX_CUDA(cudaMemcpyAsync(b + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
-        if (n_items > 0) ORBX_CUDA(cudaMemcpyAsync(b + o_ci, cell_items2, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
+    if (!dev) {
+        ORBX_CUDA(cudaMemcpyAsync(b + o_k1, keys_un1, (size_t)n1 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+        ORBX_CUDA(cudaMemcpyAsync(b + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+        if (n2 > 0) {
+            ORBX_CUDA(cudaMemcpyAsync(b + o_k2, keys_un2, (size_t)n2 * sizeof(OrbxKeyPoint), cudaMemcpyHostToDevice, st));
+            ORBX_CUDA(cudaMemcpyAsync(b + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+            if (n_items > 0) ORBX_CUDA(cudaMemcpyAsync(b + o_ci, cell_items2, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
+        }
+        ORBX_CUDA(cudaMemcpyAsync(b + o_cs, cell_start2, (ORBX_GRID_CELLS + 1) * 4, cudaMemcpyHostToDevice, st));
+        ORBX_CUDA(cudaMemcpyAsync(b + o_pv, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
     }
-    ORBX_CUDA(cudaMemcpyAsync(b + o_cs, cell_start2, (ORBX_GRID_CELLS + 1) * 4, cudaMemcpyHostToDevice, st));
-    ORBX_CUDA(cudaMemcpyAsync(b + o_pv, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
     OrbxInitArgs a;
     a.calib = *calib;
-    a.k1 = (const OrbxKeyPoint*)(b + o_k1); a.d1 = (const uint32_t*)(b + o_d1); a.n1 = n1;
-    a.k2 = (const OrbxKeyPoint*)(b + o_k2); a.d2 = (const uint32_t*)(b + o_d2); a.n2 = n2;
-    a.cell_start2 = (const int*)(b + o_cs); a.cell_items2 = (const int*)(b + o_ci);
-    a.prev = (float*)(b + o_pv); a.r = (float)window_size; a.nn_ratio = nn_ratio; a.check_orientation = check_orientation ? 1 : 0;
+    a.k1 = dev ? keys_un1 : (const OrbxKeyPoint*)(b + o_k1); a.d1 = dev ? (const uint32_t*)desc1 : (const uint32_t*)(b + o_d1); a.n1 = n1;
+    a.k2 = dev ? keys_un2 : (const OrbxKeyPoint*)(b + o_k2); a.d2 = dev ? (const uint32_t*)desc2 : (const uint32_t*)(b + o_d2); a.n2 = n2;
+    a.cell_start2 = dev ? (const int*)cell_start2 : (const int*)(b + o_cs); a.cell_items2 = dev ? (const int*)cell_items2 : (const int*)(b + o_ci);
+    a.prev = dev ? prev_matched : (float*)(b + o_pv); a.r = (float)window_size; a.nn_ratio = nn_ratio; a.check_orientation = check_orientation ? 1 : 0;
     a.sl_key = (uint4*)(b + o_sk); a.sl_idx = (uint4*)(b + o_si); a.sl_count = (int*)(b + o_sc);
-    a.matches12 = (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.act_list = (int*)(b + o_al); a.n_matches = (int*)(b + o_n);
+    a.matches12 = dev ? (int*)matches12 : (int*)(b + o_m); a.pushed = (int*)(b + o_p); a.act_list = (int*)(b + o_al); a.n_matches = (int*)(b + o_n);
     const size_t smem = (size_t)m2 * 6 + 16;
     { const int ra = set_kernel_attrs_device(h); if (ra != ORBX_OK) return ra; }
     k_init_shortlist<<<(n1 + 7) / 8, 256, 0, st>>>(a);
@@ -1650,13 +1691,23 @@ int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, c
     h->total_launches += 2; h->stage_launches += 2;
     ORBX_CUDA(cudaGetLastError());
     int nm[2] = {0, 0};
-    ORBX_CUDA(cudaMemcpyAsync(matches12, b + o_m, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(cudaMemcpyAsync(prev_matched, b + o_pv, (size_t)n1 * 8, cudaMemcpyDeviceToHost, st));
+    if (!dev) {
+        ORBX_CUDA(cudaMemcpyAsync(matches12, b + o_m, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+        ORBX_CUDA(cudaMemcpyAsync(prev_matched, b + o_pv, (size_t)n1 * 8, cudaMemcpyDeviceToHost, st));
+    }
     ORBX_CUDA(cudaMemcpyAsync(nm, b + o_n, 8, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     if (n_matches) *n_matches = nm[0];
     h->last_init_fallbacks = nm[1];
     return ORBX_OK;
+}
+
+int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1, const uint8_t* desc1, int n1,
+                                   const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2, const int32_t* cell_start2,
+                                   const int32_t* cell_items2, float* prev_matched, int window_size, float nn_ratio,
+                                   int check_orientation, int32_t* matches12, int* n_matches) {
+    return orbx_search_for_initialization_mem(h, calib, keys_un1, desc1, n1, keys_un2, desc2, n2, cell_start2, cell_items2, prev_matched,
+                                              window_size, nn_ratio, check_orientation, matches12, n_matches, ORBX_MEM_HOST);
 }
 
 // ---- CLAHE (orbx_clahe.cuh) ----

@@ -1476,6 +1476,10 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
 struct OrbxStereoArgs {
     const OrbxKeyPoint* kl; const uint32_t* dl; int nl;
     const OrbxKeyPoint* kr; const uint32_t* dr; int nr;
+    // batched form (blockIdx.y = stereo pair): per-pair strides of the keypoint / descriptor / output arrays (entries) and of the
+    // resident pyramids (bytes); counts_* = the {n, mono} pairs orbx_extract_batch wrote on the device (NULL: nl / nr above)
+    long long kp_stride; long long pyr_stride;
+    const int32_t* counts_l; const int32_t* counts_r; int cap;
     const uint8_t* pyr_l; const uint8_t* pyr_r;    // frame base of each handle's resident pyramid
     float mbf, min_d, max_d;                        // minD = 0, maxD = mbf / mb (:844-846)
     float th_mul;                                   // 1.5f * 1.4f (:979)
@@ -1487,9 +1491,16 @@ struct OrbxStereoArgs {
 #define ORBX_TH_LOW 50     // ORBmatcher::TH_LOW, :37
 
 __global__ void __launch_bounds__(256)
-k_stereo_match(const __grid_constant__ OrbxPlan plan, const OrbxStereoArgs a) {
+k_stereo_match(const __grid_constant__ OrbxPlan plan, OrbxStereoArgs a) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    {   // this block's stereo pair
+        const long long pair = blockIdx.y;
+        if (a.counts_l) { a.nl = min(max(a.counts_l[2 * pair], 0), a.cap); a.nr = min(max(a.counts_r[2 * pair], 0), a.cap); }
+        a.kl += pair * a.kp_stride; a.dl += 8 * pair * a.kp_stride; a.kr += pair * a.kp_stride; a.dr += 8 * pair * a.kp_stride;
+        a.pyr_l += pair * a.pyr_stride; a.pyr_r += pair * a.pyr_stride;
+        a.u_right += pair * a.kp_stride; a.depth += pair * a.kp_stride; a.sad += pair * a.kp_stride;
+    }
     if (iL >= a.nl) return;
     const OrbxKeyPoint kpL = a.kl[iL];
     float out_u = -1.0f, out_d = -1.0f;
@@ -1584,10 +1595,15 @@ k_stereo_match(const __grid_constant__ OrbxPlan plan, const OrbxStereoArgs a) {
 // Outlier rejection (:977-990): median of the accepted window distances (element size/2 of the ascending
 // order), threshold 1.5 * 1.4 * median, matches at or above it are dropped.  One CTA.
 __global__ void __launch_bounds__(256)
-k_stereo_filter(const OrbxStereoArgs a) {
+k_stereo_filter(OrbxStereoArgs a) {
     __shared__ int s_cnt[8];
     __shared__ int s_total;
     const int tid = threadIdx.x;
+    {
+        const long long pair = blockIdx.x;
+        if (a.counts_l) a.nl = min(max(a.counts_l[2 * pair], 0), a.cap);
+        a.u_right += pair * a.kp_stride; a.depth += pair * a.kp_stride; a.sad += pair * a.kp_stride; a.n_matched += pair;
+    }
     auto block_sum = [&](int v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ORBX_FULL_MASK, v, o);

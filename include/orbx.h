@@ -179,6 +179,15 @@ ORBX_API int orbx_stereo_match(OrbxHandle* left, OrbxHandle* right, const OrbxKe
                                const OrbxKeyPoint* keys_r, const uint8_t* desc_r, int n_r, float mb, float mbf,
                                float* u_right, float* depth, int* n_matched);
 
+/* The same row for all stereo pairs of one launch group, device-resident end to end: `left` / `right` just ran
+ * orbx_extract_batch(..., ORBX_MEM_DEVICE) on n_pairs left / right images as ONE launch group (n_pairs <= max_batch), kps_* /
+ * desc_* / counts_* are the device arrays those calls wrote (cap_per_frame entries per frame), u_right / depth (cap_per_frame
+ * floats per pair) and n_matched (one int per pair) are device arrays too.  Entries of u_right / depth beyond a pair's left
+ * keypoint count are not written.  Asynchronous on `stream` (NULL: left's own stream); nothing travels to the host. */
+ORBX_API int orbx_stereo_match_batch(OrbxHandle* left, OrbxHandle* right, int n_pairs, const OrbxKeyPoint* kps_l, const uint8_t* desc_l,
+                                     const int32_t* counts_l, const OrbxKeyPoint* kps_r, const uint8_t* desc_r, const int32_t* counts_r,
+                                     int cap_per_frame, float mb, float mbf, float* u_right, float* depth, int32_t* n_matched, void* stream);
+
 /* ---- next rows: what every Frame constructor does right after ExtractORB,
  * and the matcher that consumes it during monocular initialisation -------------------------------------------- */
 #define ORBX_FRAME_GRID_COLS 64 /* FRAME_GRID_COLS, reference inc/Frame.h:40 */
@@ -216,6 +225,15 @@ ORBX_API int orbx_search_for_initialization(OrbxHandle* h, const OrbxFrameCalib*
                                             const int32_t* cell_start2, const int32_t* cell_items2, float* prev_matched,
                                             int window_size, float nn_ratio, int check_orientation, int32_t* matches12,
                                             int* n_matches);
+
+/* The same call with every array (keypoints, descriptors, grid, prev_matched, matches12) in `mem` memory (ORBX_MEM_HOST or
+ * ORBX_MEM_DEVICE): device-resident frames -- e.g. what a fused extraction left on the GPU -- are matched where they lie,
+ * and matches12 / prev_matched stay on the device; only *n_matches (host) is read back. */
+ORBX_API int orbx_search_for_initialization_mem(OrbxHandle* h, const OrbxFrameCalib* calib, const OrbxKeyPoint* keys_un1,
+                                                const uint8_t* desc1, int n1, const OrbxKeyPoint* keys_un2, const uint8_t* desc2, int n2,
+                                                const int32_t* cell_start2, const int32_t* cell_items2, float* prev_matched,
+                                                int window_size, float nn_ratio, int check_orientation, int32_t* matches12,
+                                                int* n_matches, int mem);
 
 /* ----  the pre-processing step of the reference's demos: cv::createCLAHE(clip_limit,
  * Size(tiles_x, tiles_y))->apply(image, out) for CV_8UC1 (src/orb_extractor/main_orb_extractor.cpp:19-22,

@@ -267,3 +267,30 @@ def test_gpu_extract_frame_equals_separate_calls(oracle, gpu_ext):
         assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
         assert un.tobytes() == oun.tobytes() and np.array_equal(start, ostart) and np.array_equal(items, oitems)
         ext.close()
+
+
+@pytest.mark.gpu
+def test_gpu_search_for_initialization_device_memory(oracle, gpu_ext):
+    """orbx_search_for_initialization_mem with every array resident on the device == the host-memory call == the oracle."""
+    import torch
+    ex, ext = gpu_ext
+    w, h, K, dist = FRAME_CAMERAS["tum640"]
+    cal = ex.image_bounds(ext, *K, dist, w, h)
+    k1, d1, k2, d2 = random_frame_pair(9, 1200, 1300, w, h)
+    u1, _, _ = ex.undistort_grid(ext, cal, k1)
+    u2, s2, i2 = ex.undistort_grid(ext, cal, k2)
+    n_h, m12_h, prev_h = ex.search_for_initialization(ext, cal, u1, d1, u2, d2, s2, i2, None, 100, 0.9, True)
+    dev = torch.device("cuda")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    tu1, td1, tu2, td2, ts2, ti2 = t(u1), t(d1), t(u2), t(d2), t(s2), t(i2)
+    prev0 = np.stack([u1["x"], u1["y"]], 1).astype(np.float32)
+    tprev = t(prev0)
+    tm12 = torch.full((len(u1),), -5, dtype=torch.int32, device=dev)
+    n_d = ex.search_for_initialization_raw(ext, cal, tu1.data_ptr(), td1.data_ptr(), len(u1), tu2.data_ptr(), td2.data_ptr(), len(u2), ts2.data_ptr(),
+                                           ti2.data_ptr(), tprev.data_ptr(), 100, 0.9, True, tm12.data_ptr(), ex.MEM_DEVICE)
+    assert n_d == n_h and n_h > 50
+    assert np.array_equal(tm12.cpu().numpy(), m12_h)
+    assert np.array_equal(tprev.cpu().numpy().view(np.float32).reshape(-1, 2).view(np.uint32), prev_h.view(np.uint32))
+    ocal = oracle.make_calib(*K, dist, w, h)
+    on, om12, _ = oracle.search_for_initialization(ocal, u1, d1, u2, d2, s2, i2, None, 100, 0.9, True)
+    assert n_d == on and np.array_equal(m12_h, om12)

@@ -116,3 +116,47 @@ def test_gpu_stereo_edge_cases(oracle):
     with pytest.raises(ex.OrbxError):                        # mismatching image sizes
         ex.stereo_match(eL, other, kl, dl, kr, dr, STEREO_MB, STEREO_MBF)
     eL.close(); eR.close(); other.close()
+
+
+@pytest.mark.gpu
+def test_gpu_stereo_batch_device_resident(oracle):
+    """orbx_stereo_match_batch: three stereo pairs extracted as one launch group per camera with device outputs, matched on the
+    device with nothing travelling to the host in between.  mvuRight / mvDepth per pair == the single-pair host call (itself
+    equal to the reference goldens above) and == the oracle for one of the pairs."""
+    import torch
+    import extractorb_b200 as ex
+    lefts = np.stack([synth_frame(9, 752, 480), synth_frame(12, 752, 480), synth_frame(9, 752, 480)[::-1].copy()])
+    rights = np.stack([make_stereo_pair(l, 1 + i) for i, l in enumerate(lefts)])
+    eL, eR = ex.ORBextractor(1200, 1.2, 8, 20, 7, max_batch=3), ex.ORBextractor(1200, 1.2, 8, 20, 7, max_batch=3)
+    cap = eL.max_keypoints(752, 480)
+    dev = torch.device("cuda")
+    out = {}
+    for name, e, imgs in (("l", eL, lefts), ("r", eR, rights)):
+        d_img = torch.from_numpy(imgs).to(dev)
+        k = torch.zeros((3, cap, 7), dtype=torch.float32, device=dev)
+        d = torch.zeros((3, cap, 32), dtype=torch.uint8, device=dev)
+        c = torch.zeros((3, 2), dtype=torch.int32, device=dev)
+        e.extract_batch_raw(d_img.data_ptr(), ex.MEM_DEVICE, 3, 752, 480, 752, 752 * 480, (0, 0), k.data_ptr(), d.data_ptr(), cap, c.data_ptr(),
+                            ex.MEM_DEVICE, None)
+        out[name] = (k, d, c)
+    u = torch.full((3, cap), -7.0, dtype=torch.float32, device=dev)
+    z = torch.full((3, cap), -7.0, dtype=torch.float32, device=dev)
+    nm = torch.zeros(3, dtype=torch.int32, device=dev)
+    ex.stereo_match_batch_raw(eL, eR, 3, out["l"][0].data_ptr(), out["l"][1].data_ptr(), out["l"][2].data_ptr(), out["r"][0].data_ptr(),
+                              out["r"][1].data_ptr(), out["r"][2].data_ptr(), cap, STEREO_MB, STEREO_MBF, u.data_ptr(), z.data_ptr(), nm.data_ptr())
+    eL.synchronize()
+    u, z, nm = u.cpu().numpy(), z.cpu().numpy(), nm.cpu().numpy()
+    cl, cr = out["l"][2].cpu().numpy(), out["r"][2].cpu().numpy()
+    sL, sR = ex.ORBextractor(1200, 1.2, 8, 20, 7), ex.ORBextractor(1200, 1.2, 8, 20, 7)
+    for p in range(3):
+        _, kl, dl = sL(lefts[p], None, (0, 0))
+        _, kr, dr = sR(rights[p], None, (0, 0))
+        assert cl[p, 0] == len(kl) and cr[p, 0] == len(kr)
+        u1, z1, n1 = ex.stereo_match(sL, sR, kl, dl, kr, dr, STEREO_MB, STEREO_MBF)
+        assert np.array_equal(u[p, :len(kl)], u1) and np.array_equal(z[p, :len(kl)], z1) and nm[p] == n1, p
+        assert np.all(u[p, len(kl):] == -7.0)
+        assert n1 > 300
+    kl, dl, kr, dr, uo, do = oracle_stereo(oracle, lefts[1], rights[1])
+    assert np.array_equal(u[1, :len(kl)], uo) and np.array_equal(z[1, :len(kl)], do)
+    for e in (eL, eR, sL, sR):
+        e.close()
