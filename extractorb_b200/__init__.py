@@ -108,6 +108,7 @@ def load_library():
     L.orbx_stage_times.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.orbx_launch_count.restype = C.c_int64
     L.orbx_launch_count.argtypes = [vp]
+    L.orbx_uses_tma.argtypes = [vp]
     L.orbx_synchronize.argtypes = [vp]
     L.orbx_get_stream.restype = vp
     L.orbx_get_stream.argtypes = [vp]
@@ -306,6 +307,9 @@ class ORBextractor:
         n = C.c_int64(0)
         self._check(self._L.orbx_stage_times(self._h, ms.ctypes.data, C.byref(n)))
         return dict(zip(STAGE_NAMES, ms.tolist())), n.value
+
+    def uses_tma(self):
+        return bool(self._L.orbx_uses_tma(self._h))
 
     def launch_count(self):
         return int(self._L.orbx_launch_count(self._h))

@@ -335,7 +335,9 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
             // k_fast_tiles: the row's cells (consecutive columns from 0: cells are only ever skipped at the right end) in
             // runs of at most ORBX_FT_MAXC, balanced
             const int nv = (int)(pe->cells.size() - row_first);
-            const int ntr = (nv + ORBX_FT_MAXC - 1) / ORBX_FT_MAXC;
+            // a tile row (alignment slack + cells + 6 halo columns + the word right of the last pair) fits the 256-byte TMA box
+            const int maxc = std::max(1, std::min(ORBX_FT_MAXC, (256 - 15 - 6 - 8) / V.wCell));
+            const int ntr = (nv + maxc - 1) / maxc;
             for (int t = 0, j0 = 0; t < ntr; ++t) {
                 const int nc = nv / ntr + (t < nv % ntr ? 1 : 0);
                 const OrbxCell& a = pe->cells[row_first + j0];
@@ -405,7 +407,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.fast_trows = maxch;
     P.fast_qcap = (int)align_up((long long)(maxcw - 6) * (maxch - 6), 2);
     P.ntiles_total = (int)pe->tiles.size();
-    P.ft_tp = (int)align_up(15 + ft_maxtw + 12, 16);       // alignment slack + the word right of the last pair
+    P.ft_tp = (int)align_up(15 + ft_maxtw + 8, 16);        // alignment slack + the word right of the last pair (<= 256 for cells up to 227 px)
     P.ft_trows = ft_maxth;
     P.ft_qcap = (int)align_up(ft_qcap, 8);
     P.ft_scap = (int)align_up(ft_scap, 8);
@@ -481,7 +483,10 @@ bool build_fast_tmaps(PlanEntry* pe, uint8_t* pyr, int frames, std::vector<CUten
         else
             cudaGetLastError();
     }
-    if (!encode) return false;
+    if (!encode) {
+        if (getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled entry point not found\n");
+        return false;
+    }
     out.resize((size_t)P.nlevels);
     for (int l = 0; l < P.nlevels; ++l) {
         const OrbxLevel& V = P.lv[l];
@@ -489,9 +494,13 @@ bool build_fast_tmaps(PlanEntry* pe, uint8_t* pyr, int frames, std::vector<CUten
         const cuuint64_t strides[2] = {(cuuint64_t)V.pitch, (cuuint64_t)pe->pyr_stride};
         const cuuint32_t box[3] = {(cuuint32_t)P.ft_tp, (cuuint32_t)P.ft_trows, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
-        if (encode(&out[(size_t)l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr + V.plane_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        const CUresult cr = encode(&out[(size_t)l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr + V.plane_off, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            if (getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled(level %d) failed with CUresult %d\n", l, (int)cr);
             return false;
+        }
     }
     return true;
 }
@@ -1942,5 +1951,7 @@ int orbx_synchronize(OrbxHandle* h) {
 }
 
 void* orbx_get_stream(const OrbxHandle* h) { return h ? (void*)h->stream : nullptr; }
+
+int orbx_uses_tma(const OrbxHandle* h) { return h && h->ws_plan && h->ws.tmaps ? 1 : 0; }
 
 }  // extern "C"

@@ -255,6 +255,9 @@ ORBX_API int orbx_stage_times(OrbxHandle* h, float* ms_per_stage, int64_t* launc
 /* Total kernel launches issued by this handle since creation. */
 ORBX_API int64_t orbx_launch_count(const OrbxHandle* h);
 ORBX_API int orbx_synchronize(OrbxHandle* h);
+/* 1 if the current workspace stages its FAST tiles with TMA (cp.async.bulk.tensor through per-level tensor maps), 0 if it
+ * fell back to cp.async (tensor maps unavailable, or a cell size whose tile row exceeds the 256-byte TMA box). */
+ORBX_API int orbx_uses_tma(const OrbxHandle* h);
 /* The handle's cudaStream_t (for callers that time with their own events). */
 ORBX_API void* orbx_get_stream(const OrbxHandle* h);
 
