@@ -84,6 +84,7 @@ def load_library():
     L.orbx_get_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.orbx_get_pyramid_level.argtypes = [vp, i32, i32, vp, sz, i32]
     L.orbx_get_level_keypoints.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.orbx_get_all_level_keypoints.argtypes = [vp, i32, vp, i32, vp, C.POINTER(i32)]
     L.orbx_get_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, sz]
     L.orbx_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]

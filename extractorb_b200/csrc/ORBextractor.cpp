@@ -138,15 +138,7 @@ int ORBextractor::Extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _key
     }
     kps.resize((size_t)n);
     _keypoints.swap(kps);                                                                // fresh vector, :1112
-    if (allLevels) {                                                                     // :1094 (level coordinates)
-        allLevels->assign((size_t)nlevels, std::vector<cv::KeyPoint>());
-        for (int l = 0; l < nlevels; ++l) {
-            int nl = 0;
-            orbx_get_level_keypoints(mpHandle, 0, l, nullptr, 0, &nl);
-            (*allLevels)[l].resize((size_t)nl);
-            if (nl) orbx_get_level_keypoints(mpHandle, 0, l, reinterpret_cast<OrbxKeyPoint*>((*allLevels)[l].data()), nl, &nl);
-        }
-    }
+    if (allLevels && !FetchAllLevels(*allLevels, cap)) { mLastError = orbx_last_error(mpHandle); return -1; }   // :1094
     if (mbDownloadPyramid && !DownloadPyramid()) { mLastError = orbx_last_error(mpHandle); return -1; }
     return mono;                                                                         // monoIndex, :1161
 }
@@ -172,17 +164,33 @@ void ORBextractor::ComputePyramid(cv::Mat image) {
     DownloadPyramid();
 }
 
+// allKeypoints (level coordinates, angle set) of the resident frame: one read-back for all levels.
+bool ORBextractor::FetchAllLevels(std::vector<std::vector<cv::KeyPoint> >& all, int cap) {
+    all.assign((size_t)nlevels, std::vector<cv::KeyPoint>());
+    if (cap <= 0) {
+        int w0 = 0, h0 = 0;
+        if (orbx_get_level_size(mpHandle, 0, &w0, &h0) != ORBX_OK) return false;
+        cap = orbx_max_keypoints(mpHandle, w0, h0);
+        if (cap <= 0) return false;
+    }
+    std::vector<cv::KeyPoint> flat((size_t)cap);
+    std::vector<int32_t> counts((size_t)nlevels, 0);
+    int total = 0;
+    if (orbx_get_all_level_keypoints(mpHandle, 0, reinterpret_cast<OrbxKeyPoint*>(flat.data()), cap, counts.data(), &total) != ORBX_OK) return false;
+    size_t at = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        all[(size_t)l].assign(flat.begin() + at, flat.begin() + at + (size_t)counts[(size_t)l]);
+        at += (size_t)counts[(size_t)l];
+    }
+    return true;
+}
+
 void ORBextractor::ComputeKeyPointsOctTree(std::vector<std::vector<cv::KeyPoint> >& allKeypoints) {
     allKeypoints.assign((size_t)nlevels, std::vector<cv::KeyPoint>());                   // :775
     if (!EnsureHandle()) return;
     if (orbx_compute_keypoints_octtree(mpHandle) != ORBX_OK) { mLastError = orbx_last_error(mpHandle); return; }
     mLastError.clear();
-    for (int l = 0; l < nlevels; ++l) {
-        int nl = 0;
-        orbx_get_level_keypoints(mpHandle, 0, l, nullptr, 0, &nl);
-        allKeypoints[l].resize((size_t)nl);
-        if (nl) orbx_get_level_keypoints(mpHandle, 0, l, reinterpret_cast<OrbxKeyPoint*>(allKeypoints[l].data()), nl, &nl);
-    }
+    if (!FetchAllLevels(allKeypoints, 0)) mLastError = orbx_last_error(mpHandle);
 }
 
 std::vector<cv::KeyPoint> ORBextractor::DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX,

@@ -1906,6 +1906,41 @@ int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* 
     return ORBX_OK;
 }
 
+// allKeypoints of every level with one read-back (the 6-argument operator() hands them all to its caller, :1094): the frame's
+// whole keypoint-record block and its level counts travel in two copies into pinned memory instead of two per level.
+int orbx_get_all_level_keypoints(OrbxHandle* h, int frame, OrbxKeyPoint* kps, int capacity, int32_t* counts, int* n_total) {
+    int rc = check_frame(h, frame, 0);
+    if (rc != ORBX_OK) return rc;
+    if (n_total) *n_total = 0;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const OrbxPlan& P = h->cur->plan;
+    const size_t rec_bytes = (size_t)P.kp_total * sizeof(OrbxKpRec), cnt_bytes = (size_t)P.nlevels * sizeof(int2);
+    const size_t o_cnt = (size_t)align_up((long long)rec_bytes, 256);
+    rc = ensure_bytes(h, (void**)&h->h_frame, &h->h_frame_bytes, o_cnt + cnt_bytes, true);
+    if (rc != ORBX_OK) return rc;
+    const OrbxWs& w = res_ws(h);
+    ORBX_CUDA(cudaMemcpyAsync(h->h_frame, w.kprec + (size_t)frame * w.kp_stride, rec_bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_frame + o_cnt, w.level_count + (size_t)frame * P.nlevels, cnt_bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    const OrbxKpRec* rec = reinterpret_cast<const OrbxKpRec*>(h->h_frame);
+    const int2* lc = reinterpret_cast<const int2*>(h->h_frame + o_cnt);
+    int total = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        const OrbxLevel& V = P.lv[l];
+        const int n = std::min(std::max(lc[l].x, 0), V.kp_cap);
+        if (counts) counts[l] = n;
+        for (int i = 0; i < n; ++i, ++total) {
+            if (!kps || total >= capacity) continue;
+            const OrbxKpRec& r = rec[V.kp_off + i];
+            OrbxKeyPoint& k = kps[total];
+            k.x = r.x; k.y = r.y; k.size = V.kp_size; k.angle = r.angle; k.response = r.response; k.octave = l; k.class_id = -1;
+        }
+    }
+    if (n_total) *n_total = total;
+    if (kps && total > capacity) return fail(h, ORBX_ERR_CAPACITY, "keypoint capacity too small");
+    return ORBX_OK;
+}
+
 int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores, uint32_t* order,
                               int capacity, int* n_out) {
     int rc = check_frame(h, frame, level);

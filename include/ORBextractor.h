@@ -101,6 +101,7 @@ public:
 private:
     bool EnsureHandle();
     bool DownloadPyramid();
+    bool FetchAllLevels(std::vector<std::vector<cv::KeyPoint> >& all, int cap);
     int Extract(cv::InputArray image, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors,
                 std::vector<int>& vLappingArea, std::vector<std::vector<cv::KeyPoint> >* allLevels);
 

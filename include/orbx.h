@@ -161,6 +161,9 @@ ORBX_API void* orbx_host_alloc(size_t bytes, int write_combined);
 ORBX_API void orbx_host_free(void* p);
 /* allKeypoints[level] in level coordinates with angle set (== allLevelsKeypoints, ORBextractor.cc:1094). */
 ORBX_API int orbx_get_level_keypoints(OrbxHandle* h, int frame, int level, OrbxKeyPoint* kps, int capacity, int* n_out);
+/* The same for every level in one call and one read-back: kps receives the levels back to back (level l contributes counts[l]
+ * entries), *n_total their sum; capacity >= orbx_max_keypoints() always suffices. */
+ORBX_API int orbx_get_all_level_keypoints(OrbxHandle* h, int frame, OrbxKeyPoint* kps, int capacity, int32_t* counts, int* n_total);
 /* FAST candidates of the cell loop (ORBextractor.cc:855-860): x, y relative to (16,16), score, and the
  * emission-order key (cell row, cell col, y, x).  Storage order is unspecified; sort by `order`. */
 ORBX_API int orbx_get_level_candidates(OrbxHandle* h, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores,

@@ -403,17 +403,21 @@ def test_fast_v1_v2_same_candidates(gpu, monkeypatch):
             if kind == "low":
                 img = (img // 10 + 90).astype(np.uint8)
         out = []
-        for v1 in ("1", "0"):
+        for v1, tma in (("1", "1"), ("0", "1"), ("0", "0")):       # round-1 kernel, tile kernel with TMA staging, with cp.async staging
             monkeypatch.setenv("ORBX_FAST_V1", v1)
+            monkeypatch.setenv("ORBX_FAST_TMA", tma)
             e = gpu.ORBextractor(1500, 1.2, 4, 20, 7, cell_size=cell)
             ret, kps, desc = e(img, None, (0, 0))
+            assert e.uses_tma() == (tma == "1"), "TMA staging must be engaged on this GPU unless switched off (every tile row fits the 256-byte box)"
             out.append(([e.level_candidates(l) for l in range(4)], kps, desc))
             e.close()
         monkeypatch.delenv("ORBX_FAST_V1")
-        for l in range(4):
-            for a, b in zip(out[0][0][l], out[1][0][l]):
-                assert np.array_equal(a, b), (w, h, cell, kind, l)
-        assert kp_bytes_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+        monkeypatch.delenv("ORBX_FAST_TMA")
+        for other in (1, 2):
+            for l in range(4):
+                for a, b in zip(out[0][0][l], out[other][0][l]):
+                    assert np.array_equal(a, b), (w, h, cell, kind, l, other)
+            assert kp_bytes_equal(out[0][1], out[other][1]) and np.array_equal(out[0][2], out[other][2])
 
 
 def test_extract_batch_multi_two_handles(gpu):
