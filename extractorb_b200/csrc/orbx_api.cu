@@ -51,6 +51,7 @@ struct PlanEntry {
     uint32_t* d_blur_tiles = nullptr;
     long long pyr_stride = 0, blur_stride = 0, cand_stride = 0;
     size_t fast_smem = 0, qt_smem = 0;
+    bool qt_global = false;                 // quadtree node tables in HBM (ws.qt_scratch) instead of shared memory
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
@@ -423,8 +424,14 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     pe->blur_stride = align_up(blur_off, 256);
     pe->cand_stride = align_up(cand_off, 4);
     pe->fast_smem = (size_t)ORBX_FAST_WARPS * (size_t)align_up(2 * align_up((long long)P.fast_tp * P.fast_trows, 16) + 2ll * P.fast_qcap, 16);
-    pe->qt_smem = (size_t)qt_nc * 64;
-    if (pe->qt_smem > 200 * 1024 || qt_nc > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "nfeatures per level too large for the quadtree kernel's shared memory"); }
+    P.qt_sk = 1;
+    while (P.qt_sk < qt_nc) P.qt_sk <<= 1;
+    P.qt_bytes = align_up((long long)orbx_qt_bytes(qt_nc), 16);
+    // node tables in shared memory while they fit (with room for several CTAs per SM); beyond that -- tens of thousands of features
+    // on one level -- every (frame, level) tree gets a block of HBM instead (alloc_ws_set), the kernel is the same
+    pe->qt_global = P.qt_bytes > 160 * 1024;
+    pe->qt_smem = pe->qt_global ? 0 : (size_t)P.qt_bytes;
+    if (qt_nc > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "more than 65533 features on one level (quadtree nodes are indexed with 16 bits)"); }
     if (pe->fast_smem > 200 * 1024) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
     std::vector<uint32_t> btiles;
     for (int l = 0; l < L; ++l)
@@ -449,7 +456,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
 }
 
 void free_ws_set(OrbxWs& w, bool own_flags) {
-    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps));
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps)); cudaFree(w.qt_scratch);
     cudaFree(w.kprec); cudaFree(w.cand_count); cudaFree(w.level_count);
     if (own_flags) cudaFree(w.flags);
     memset(&w, 0, sizeof(w));
@@ -516,6 +523,8 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
         ORBX_CUDA(cudaMemset(w.blur, 0x5A, (size_t)pe->blur_stride * frames));
     }
     ORBX_CUDA(cudaMalloc(&w.kprec, (size_t)P.kp_total * frames * sizeof(OrbxKpRec)));
+    w.qt_scratch = nullptr;
+    if (pe->qt_global) ORBX_CUDA(cudaMalloc(&w.qt_scratch, (size_t)P.qt_bytes * P.nlevels * frames));
     ORBX_CUDA(cudaMalloc(&w.cand_count, (size_t)P.nlevels * frames * sizeof(int)));
     ORBX_CUDA(cudaMalloc(&w.level_count, (size_t)P.nlevels * frames * sizeof(int2)));
     if (shared_flags) {
@@ -640,7 +649,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             k_fast_tiles<true><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         else if (V.ntiles > 0)
             k_fast_tiles<false><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
-        k_octree<ORBX_QT_THREADS_BIG><<<dim3(1, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
+        k_octree<ORBX_QT_THREADS_BIG><<<dim3(nf, 1), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
         launches += 2;
         ORBX_CUDA(cudaEventRecord(h->ev_lvl_done[l], sl));
         return ORBX_OK;
@@ -723,13 +732,13 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         // levels of a megapixel or more hold tens of thousands of candidates each: their quadtrees get 1024-thread CTAs
         const int nbig = qt_big_levels(P);
         if (nbig > 0) {
-            k_octree<ORBX_QT_THREADS_BIG><<<dim3(nbig, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, 0);
+            k_octree<ORBX_QT_THREADS_BIG><<<dim3(nf, nbig), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, 0);
             ++launches;
         }
         if (nbig < P.nlevels) {
-            if (nf <= 2) k_octree<ORBX_QT_THREADS_BIG><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, nbig);
-            else if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws, nbig);
-            else k_octree<ORBX_QT_THREADS><<<dim3(P.nlevels - nbig, nf), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws, nbig);
+            if (nf <= 2) k_octree<ORBX_QT_THREADS_BIG><<<dim3(nf, P.nlevels - nbig), ORBX_QT_THREADS_BIG, pe->qt_smem, st>>>(P, ws, nbig);
+            else if (nf <= 8) k_octree<ORBX_QT_THREADS_LAT><<<dim3(nf, P.nlevels - nbig), ORBX_QT_THREADS_LAT, pe->qt_smem, st>>>(P, ws, nbig);
+            else k_octree<ORBX_QT_THREADS><<<dim3(nf, P.nlevels - nbig), ORBX_QT_THREADS, pe->qt_smem, st>>>(P, ws, nbig);
             ++launches;
         }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[3], st));
@@ -1416,13 +1425,17 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     V.cand_cap = std::max(n, 1); V.cand_off = 0;
     V.kp_cap = std::max(n_features + 2, 4 * nIni) + 2; V.kp_off = 0; V.sf = 1.f;
     P.kp_total = V.kp_cap; P.qt_nc = V.kp_cap + 2;
-    const size_t smem = (size_t)P.qt_nc * 64;
-    if (smem > 200 * 1024) return fail(h, ORBX_ERR_BAD_ARGUMENT, "n_features too large for the quadtree kernel");
+    if (P.qt_nc > 65535) return fail(h, ORBX_ERR_BAD_ARGUMENT, "n_features too large (quadtree nodes are indexed with 16 bits)");
+    P.qt_sk = 1;
+    while (P.qt_sk < P.qt_nc) P.qt_sk <<= 1;
+    P.qt_bytes = align_up((long long)orbx_qt_bytes(P.qt_nc), 16);
+    const bool qt_global = P.qt_bytes > 160 * 1024;
+    const size_t smem = qt_global ? 0 : (size_t)P.qt_bytes;
     OrbxWs w;
     memset(&w, 0, sizeof(w));
     int rc = ORBX_OK;
-    uint2* d_cand = nullptr; uint16_t* d_kn = nullptr; OrbxKpRec* d_rec = nullptr; int* d_cnt = nullptr; int2* d_lc = nullptr;
-    auto cleanup = [&]() { cudaFree(d_cand); cudaFree(d_kn); cudaFree(d_rec); cudaFree(d_cnt); cudaFree(d_lc); };
+    uint2* d_cand = nullptr; uint16_t* d_kn = nullptr; OrbxKpRec* d_rec = nullptr; int* d_cnt = nullptr; int2* d_lc = nullptr; uint8_t* d_qt = nullptr;
+    auto cleanup = [&]() { cudaFree(d_cand); cudaFree(d_kn); cudaFree(d_rec); cudaFree(d_cnt); cudaFree(d_lc); cudaFree(d_qt); };
 #define ORBX_CUDA_L(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(h, ORBX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     ORBX_CUDA_L(cudaMalloc(&d_cand, cand.size() * sizeof(uint2)));
     ORBX_CUDA_L(cudaMalloc(&d_kn, cand.size() * sizeof(uint16_t)));
@@ -1431,7 +1444,8 @@ int orbx_distribute_octtree(OrbxHandle* h, const OrbxKeyPoint* keys, int n, int 
     ORBX_CUDA_L(cudaMalloc(&d_lc, sizeof(int2)));
     ORBX_CUDA_L(cudaMemcpyAsync(d_cand, cand.data(), cand.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
     ORBX_CUDA_L(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc;
+    if (qt_global) ORBX_CUDA_L(cudaMalloc(&d_qt, (size_t)P.qt_bytes));
+    w.cand = d_cand; w.keynode = d_kn; w.kprec = d_rec; w.cand_count = d_cnt; w.level_count = d_lc; w.qt_scratch = d_qt;
     w.cand_stride = (long long)cand.size(); w.kp_stride = V.kp_cap;
     { const int ra = set_kernel_attrs_device(h); if (ra != ORBX_OK) { cleanup(); return ra; } }
     k_octree<ORBX_QT_THREADS_LAT><<<dim3(1, 1), ORBX_QT_THREADS_LAT, smem, h->stream>>>(P, w, 0);

@@ -793,7 +793,8 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         }
         cflags = __reduce_or_sync(ORBX_FULL_MASK, cflags);
         if (lane == 0 && cflags) atomicOr(&s_flags, (int)cflags);
-        // ---- emission: one atomic per warp reserves the slots; entries carry the emission-order key (:855-860) ----
+        // ---- emission: one atomic per warp reserves the slots; entries carry the emission-order key (:855-860).  (One atomic
+        // per tile through a shared counter and two more barriers was slower, also at 4K: 507 vs 478 us, 2.09 vs 1.98 ms.) ----
         if (nsv > 0) {
             int slot0 = 0;
             if (lane == 0) {
@@ -842,17 +843,6 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
 #define ORBX_QT_THREADS_BIG 1024 // levels of >= ORBX_QT_BIG_PIXELS pixels (tens of thousands of candidates per quadtree)
 #define ORBX_QT_BIG_PIXELS 1000000
 
-struct QtShared {
-    short4* rect[2];  // x0, x1, y0, y1
-    int* cnt[2];
-    int* cc;          // 4 child counts per node (reused as 64-bit argmax slots at the end)
-    int* seq;         // processing sequence (list positions)
-    int* tmp;         // children per sequence entry -> exclusive scan
-    int* cbase;       // creation index of the first child, -1 if the node is not split this pass
-    int* surv;        // survivor flag -> new list position
-    unsigned long long* skey;  // careful-phase sort keys
-};
-
 __device__ __forceinline__ int qt_quadrant(short4 r, int x, int y) {
     const int mx = r.x + ((r.y - r.x + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2), :488
     const int my = r.z + ((r.w - r.z + 1) >> 1);
@@ -899,6 +889,42 @@ __device__ int block_excl_scan(int* v, int n, int* scratch) {
     return total;
 }
 
+// Bytes of node storage per quadtree (rect x2, cnt x2, child counts x2, seq / tmp / cbase / surv, sort keys padded to a power
+// of two).  Small trees keep it in shared memory; a tree too big for that (tens of thousands of features on one level) runs
+// from a per-(frame, level) block of ws.qt_scratch instead -- same code, generic pointers.
+#define ORBX_QT_NODE_BYTES 72
+__host__ __device__ inline size_t orbx_qt_bytes(int nc) {
+    int sk = 1;
+    while (sk < nc) sk <<= 1;
+    return (size_t)nc * ORBX_QT_NODE_BYTES + (size_t)sk * 8;
+}
+
+// One sweep over a tree's candidates with several independent global loads in flight per thread (a quadtree is one CTA: its
+// candidate list lives in L2 / HBM, and the sweep is bound by load latency, not by instructions).  f(k, node, xy) per candidate.
+#define ORBX_QT_MLP 4
+template <int NT, typename F>
+__device__ __forceinline__ void qt_sweep(const uint2* __restrict__ cand, const uint16_t* __restrict__ keynode, int ncand, F f) {
+    for (int b0 = 0; b0 < ncand; b0 += ORBX_QT_MLP * NT) {           // uniform trip count: f may use warp-wide primitives
+        const int base = b0 + (int)threadIdx.x;
+        int pos[ORBX_QT_MLP];
+        uint32_t v[ORBX_QT_MLP];
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j) {
+            const int k = base + j * NT;
+            pos[j] = k < ncand ? (int)keynode[k] : -1;
+            v[j] = k < ncand ? cand[k].x : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j) f(base + j * NT, pos[j], v[j]);     // f is called by every lane (pos < 0: no candidate)
+    }
+}
+
+// Warp-aggregated atomicAdd(&cc[key], 1): lanes holding the same key add once.  key < 0: nothing.  All lanes of the warp call it.
+__device__ __forceinline__ void qt_count(int* cc, int key) {
+    const unsigned peers = __match_any_sync(ORBX_FULL_MASK, key);
+    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cc[key], __popc(peers));
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level_base) {
@@ -906,26 +932,27 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
     __shared__ int s_scratch[33];
     __shared__ int s_nexp, s_cut, s_state;
 
-    const int level = level_base + blockIdx.x, frame = blockIdx.y;
+    // grid (frames, levels): CTAs are handed out level-major, the biggest trees (level 0) first -- the longest jobs start first
+    const int level = level_base + blockIdx.y, frame = blockIdx.x;
     const OrbxLevel& L = plan.lv[level];
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int tid = threadIdx.x;
+    constexpr int nt = NT;
     const int NC = plan.qt_nc;
     const int N = L.N;
 
-    QtShared q;
-    {
-        uint8_t* p = smem_qt;
-        q.cc = reinterpret_cast<int*>(p); p += (size_t)NC * 16;      // first: read as int4 (16-byte aligned)
-        q.skey = reinterpret_cast<unsigned long long*>(p); p += (size_t)NC * 8;
-        q.rect[0] = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;
-        q.rect[1] = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;
-        q.cnt[0] = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
-        q.cnt[1] = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
-        q.seq = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
-        q.tmp = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
-        q.cbase = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
-        q.surv = reinterpret_cast<int*>(p);
-    }
+    // node storage: shared memory, or this tree's block of the global scratch when the plan's trees do not fit
+    uint8_t* p = ws.qt_scratch ? ws.qt_scratch + ((size_t)frame * plan.nlevels + level) * plan.qt_bytes : smem_qt;
+    int* ccA = reinterpret_cast<int*>(p); p += (size_t)NC * 16;      // 4 child counts per node of the current list (int4 reads)
+    int* ccB = reinterpret_cast<int*>(p); p += (size_t)NC * 16;      // ... of the list under construction
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(p); p += (size_t)plan.qt_sk * 8;
+    short4* rectA = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;   // x0, x1, y0, y1
+    short4* rectB = reinterpret_cast<short4*>(p); p += (size_t)NC * 8;
+    int* cntA = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
+    int* cntB = reinterpret_cast<int*>(p); p += (size_t)NC * 4;
+    int* seq = reinterpret_cast<int*>(p); p += (size_t)NC * 4;       // processing sequence (list positions)
+    int* tmp = reinterpret_cast<int*>(p); p += (size_t)NC * 4;       // children per sequence entry -> exclusive scan
+    int* cbase = reinterpret_cast<int*>(p); p += (size_t)NC * 4;     // creation index of the first child, -1 if the node is not split this pass
+    int* surv = reinterpret_cast<int*>(p);                           // survivor flag -> new list position
 
     const int ncand = min(ws.cand_count[frame * plan.nlevels + level], L.cand_cap);
     const uint2* cand = ws.cand + (long long)frame * ws.cand_stride + L.cand_off;
@@ -933,156 +960,178 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
     const int CM = (1 << ORBX_COORD_BITS) - 1;
 
     // ---- initial nodes (:548-590): assign by float division, drop the empty ones ----
-    int cur = 0;
     for (int i = tid; i < L.nIni; i += nt) {
-        q.rect[0][i] = make_short4((short)(int)__fmul_rn(L.hX, (float)i), (short)(int)__fmul_rn(L.hX, (float)(i + 1)),
-                                   0, (short)L.span_y);
-        q.cnt[0][i] = 0;
+        rectA[i] = make_short4((short)(int)__fmul_rn(L.hX, (float)i), (short)(int)__fmul_rn(L.hX, (float)(i + 1)), 0, (short)L.span_y);
+        cntA[i] = 0;
     }
     __syncthreads();
-    for (int k = tid; k < ncand; k += nt) {
-        const int x = cand[k].x & CM;
-        const int r = (int)__fdiv_rn((float)x, L.hX);
-        keynode[k] = (uint16_t)r;
-        atomicAdd(&q.cnt[0][r], 1);
-    }
-    __syncthreads();
-    for (int i = tid; i < L.nIni; i += nt) q.surv[i] = q.cnt[0][i] > 0;
-    __syncthreads();
-    int nlive = block_excl_scan(q.surv, L.nIni, s_scratch);
-    for (int i = tid; i < L.nIni; i += nt)
-        if (q.cnt[0][i] > 0) {
-            q.rect[1][q.surv[i]] = q.rect[0][i];
-            q.cnt[1][q.surv[i]] = q.cnt[0][i];
+    for (int b0 = 0; b0 < ncand; b0 += ORBX_QT_MLP * nt) {
+        const int base = b0 + tid;
+        uint32_t v[ORBX_QT_MLP];
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j) v[j] = base + j * nt < ncand ? cand[base + j * nt].x : 0u;
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j) {
+            const int k = base + j * nt;
+            int r = -1;
+            if (k < ncand) {
+                r = (int)__fdiv_rn((float)(int)(v[j] & CM), L.hX);
+                keynode[k] = (uint16_t)r;
+            }
+            qt_count(cntA, r);
         }
-    for (int k = tid; k < ncand; k += nt) keynode[k] = (uint16_t)q.surv[keynode[k]];
-    cur = 1;
+    }
     __syncthreads();
+    for (int i = tid; i < L.nIni; i += nt) surv[i] = cntA[i] > 0;
+    __syncthreads();
+    int nlive = block_excl_scan(surv, L.nIni, s_scratch);
+    for (int i = tid; i < L.nIni; i += nt)
+        if (cntA[i] > 0) {
+            rectB[surv[i]] = rectA[i];
+            cntB[surv[i]] = cntA[i];
+        }
+    for (int i = tid; i < 4 * nlive; i += nt) ccB[i] = 0;
+    __syncthreads();
+    // keys move to the compacted initial list; child occupancy of every node that can still be split
+    qt_sweep<NT>(cand, keynode, ncand, [&](int k, int pos, uint32_t v) {
+        int key = -1;
+        if (pos >= 0) {
+            const int np = surv[pos];
+            keynode[k] = (uint16_t)np;
+            if (cntB[np] > 1) key = 4 * np + qt_quadrant(rectB[np], (int)(v & CM), (int)((v >> ORBX_COORD_BITS) & CM));
+        }
+        qt_count(ccB, key);
+    });
+    __syncthreads();
+    // current list: (rect, cnt, cc); list under construction: (nrect, ncnt, ncc)
+    short4 *rect = rectB, *nrect = rectA;
+    int *cnt = cntB, *ncnt = cntA, *cc = ccB, *ncc = ccA;
 
     bool careful = false;
     for (;;) {
         const int prev_size = nlive;
-        const short4* rect = q.rect[cur];
-        const int* cnt = q.cnt[cur];
         // ---- processing sequence: live nodes holding > 1 key, in list order ----
-        for (int i = tid; i < nlive; i += nt) {
-            q.tmp[i] = cnt[i] > 1;
-            q.cc[4 * i + 0] = 0; q.cc[4 * i + 1] = 0; q.cc[4 * i + 2] = 0; q.cc[4 * i + 3] = 0;
-        }
+        for (int i = tid; i < nlive; i += nt) tmp[i] = cnt[i] > 1;
         if (tid == 0) { s_nexp = 0; s_cut = -1; }
         __syncthreads();
-        const int ns = block_excl_scan(q.tmp, nlive, s_scratch);
+        const int ns = block_excl_scan(tmp, nlive, s_scratch);
         if (ns == 0) break;  // every node is a single key: list size unchanged -> finish (:674)
         for (int i = tid; i < nlive; i += nt)
-            if (cnt[i] > 1) q.seq[q.tmp[i]] = i;
+            if (cnt[i] > 1) seq[tmp[i]] = i;
         __syncthreads();
         if (careful) {
-            // (size desc, later-created first) == (size desc, list position asc); rank sort
-            for (int s = tid; s < ns; s += nt) {
-                const int pos = q.seq[s];
-                q.skey[s] = ((unsigned long long)(unsigned)cnt[pos] << 32) | (unsigned)(0x7fffffff - pos);
-            }
-            __syncthreads();
-            for (int s = tid; s < ns; s += nt) {
-                const unsigned long long key = q.skey[s];
-                int rank = 0;
-                for (int t = 0; t < ns; ++t) rank += q.skey[t] > key;
-                q.tmp[rank] = 0x7fffffff - (int)(unsigned)(key & 0xffffffffu);
-            }
-            __syncthreads();
-            for (int s = tid; s < ns; s += nt) q.seq[s] = q.tmp[s];
-            __syncthreads();
-        }
-        // ---- child occupancy of every node in the sequence ----
-        for (int base = 0; base < ncand; base += nt) {
-            const int k = base + tid;
-            int key = -1;
-            if (k < ncand) {
-                const int pos = keynode[k];
-                if (cnt[pos] > 1) {
-                    const uint32_t v = cand[k].x;
-                    key = 4 * pos + qt_quadrant(rect[pos], (int)(v & CM), (int)((v >> ORBX_COORD_BITS) & CM));
+            // (size desc, later-created first) == (size desc, list position asc): bitonic sort of 64-bit keys, zero-padded
+            int n2 = 1;
+            while (n2 < ns) n2 <<= 1;
+            for (int s_ = tid; s_ < n2; s_ += nt) {
+                unsigned long long key = 0ull;
+                if (s_ < ns) {
+                    const int pos = seq[s_];
+                    key = ((unsigned long long)(unsigned)cnt[pos] << 32) | (unsigned)(0x7fffffff - pos);
                 }
+                skey[s_] = key;
             }
-            const unsigned peers = __match_any_sync(ORBX_FULL_MASK, key);
-            if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&q.cc[key], __popc(peers));
+            __syncthreads();
+            for (int size = 2; size <= n2; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = tid; t < (n2 >> 1); t += nt) {
+                        const int i = 2 * t - (t & (stride - 1));          // lower index of the pair
+                        const int j = i + stride;
+                        const unsigned long long a = skey[i], b = skey[j];
+                        const bool desc = (i & size) == 0;                 // descending blocks first: the whole array ends descending
+                        if ((a < b) == desc) { skey[i] = b; skey[j] = a; }
+                    }
+                    __syncthreads();
+                }
+            for (int s_ = tid; s_ < ns; s_ += nt) seq[s_] = 0x7fffffff - (int)(unsigned)(skey[s_] & 0xffffffffu);
+            __syncthreads();
         }
-        __syncthreads();
-        for (int s = tid; s < ns; s += nt) {
-            const int pos = q.seq[s];
-            q.tmp[s] = (q.cc[4 * pos] > 0) + (q.cc[4 * pos + 1] > 0) + (q.cc[4 * pos + 2] > 0) + (q.cc[4 * pos + 3] > 0);
+        // ---- children of every node in the sequence (occupancy was counted when the node was created) ----
+        for (int s_ = tid; s_ < ns; s_ += nt) {
+            const int4 c4 = *reinterpret_cast<const int4*>(cc + 4 * seq[s_]);
+            tmp[s_] = (c4.x > 0) + (c4.y > 0) + (c4.z > 0) + (c4.w > 0);
         }
-        if (tid == 0) q.tmp[ns] = 0;
+        if (tid == 0) tmp[ns] = 0;
         __syncthreads();
-        const int tall = block_excl_scan(q.tmp, ns + 1, s_scratch);  // tmp[s] = children created before split s
+        block_excl_scan(tmp, ns + 1, s_scratch);  // tmp[s] = children created before split s
         // ---- how many splits are applied (careful phase stops once the list reaches N, :735) ----
         int nsplit = ns;
         if (careful) {
             for (int j = tid + 1; j <= ns; j += nt) {
-                const bool now = prev_size + q.tmp[j] - j >= N;
-                const bool before = prev_size + q.tmp[j - 1] - (j - 1) >= N;
+                const bool now = prev_size + tmp[j] - j >= N;
+                const bool before = prev_size + tmp[j - 1] - (j - 1) >= N;
                 if (now && !before) s_cut = j;
             }
             __syncthreads();
             if (s_cut > 0) nsplit = s_cut;
         }
-        const int T = q.tmp[nsplit];  // children created this pass
-        (void)tall;
-        for (int i = tid; i < nlive; i += nt) { q.cbase[i] = -1; q.surv[i] = 1; }
+        const int T = tmp[nsplit];  // children created this pass
+        for (int i = tid; i < nlive; i += nt) { cbase[i] = -1; surv[i] = 1; }
         __syncthreads();
-        for (int s = tid; s < nsplit; s += nt) {
-            const int pos = q.seq[s];
-            q.cbase[pos] = q.tmp[s];
-            q.surv[pos] = 0;
+        for (int s_ = tid; s_ < nsplit; s_ += nt) {
+            const int pos = seq[s_];
+            cbase[pos] = tmp[s_];
+            surv[pos] = 0;
         }
         __syncthreads();
-        const int nsurv = block_excl_scan(q.surv, nlive, s_scratch);
-        short4* nrect = q.rect[cur ^ 1];
-        int* ncnt = q.cnt[cur ^ 1];
+        const int nsurv = block_excl_scan(surv, nlive, s_scratch);
         // children: list position T-1-(creation index); DivideNode geometry :488-514
-        for (int s = tid; s < nsplit; s += nt) {
-            const int pos = q.seq[s];
+        for (int s_ = tid; s_ < nsplit; s_ += nt) {
+            const int pos = seq[s_];
             const short4 r = rect[pos];
             const int mx = r.x + ((r.y - r.x + 1) >> 1), my = r.z + ((r.w - r.z + 1) >> 1);
-            int ci = q.tmp[s];
+            const int4 c4 = *reinterpret_cast<const int4*>(cc + 4 * pos);
+            const int nn[4] = {c4.x, c4.y, c4.z, c4.w};
+            int ci = tmp[s_];
             int nexp = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int n = q.cc[4 * pos + c];
+                const int n = nn[c];
                 if (n > 0) {
                     const int np = T - 1 - ci;
                     nrect[np] = make_short4((short)((c & 1) ? mx : r.x), (short)((c & 1) ? r.y : mx),
                                             (short)((c & 2) ? my : r.z), (short)((c & 2) ? r.w : my));
                     ncnt[np] = n;
+                    *reinterpret_cast<int4*>(ncc + 4 * np) = make_int4(0, 0, 0, 0);
                     nexp += n > 1;
                     ++ci;
                 }
             }
             if (nexp) atomicAdd(&s_nexp, nexp);
         }
+        // untouched nodes keep their rectangle, count and child occupancy
         for (int i = tid; i < nlive; i += nt)
-            if (q.cbase[i] < 0) {
-                nrect[T + q.surv[i]] = rect[i];
-                ncnt[T + q.surv[i]] = cnt[i];
+            if (cbase[i] < 0) {
+                const int np = T + surv[i];
+                nrect[np] = rect[i];
+                ncnt[np] = cnt[i];
+                *reinterpret_cast<int4*>(ncc + 4 * np) = *reinterpret_cast<const int4*>(cc + 4 * i);
             }
-        // keys follow their node
-        for (int k = tid; k < ncand; k += nt) {
-            const int pos = keynode[k];
-            const int cb = q.cbase[pos];
-            int np;
-            if (cb >= 0) {
-                const uint32_t v = cand[k].x;
-                const int c = qt_quadrant(rect[pos], (int)(v & CM), (int)((v >> ORBX_COORD_BITS) & CM));
-                const int4 cc4 = *reinterpret_cast<const int4*>(q.cc + 4 * pos);
-                const unsigned occ = (cc4.x > 0) | ((cc4.y > 0) << 1) | ((cc4.z > 0) << 2) | ((cc4.w > 0) << 3);
-                np = T - 1 - (cb + __popc(occ & ((1u << c) - 1u)));
-            } else {
-                np = T + q.surv[pos];
-            }
-            keynode[k] = (uint16_t)np;
-        }
         __syncthreads();
-        cur ^= 1;
+        // keys follow their node, and count the occupancy of the new node's own children on the way
+        qt_sweep<NT>(cand, keynode, ncand, [&](int k, int pos, uint32_t v) {
+            int key = -1;
+            if (pos >= 0) {
+                const int cb = cbase[pos];
+                int np;
+                if (cb >= 0) {
+                    const int x = (int)(v & CM), y = (int)((v >> ORBX_COORD_BITS) & CM);
+                    const int c = qt_quadrant(rect[pos], x, y);
+                    const int4 cc4 = *reinterpret_cast<const int4*>(cc + 4 * pos);
+                    const unsigned occ = (cc4.x > 0) | ((cc4.y > 0) << 1) | ((cc4.z > 0) << 2) | ((cc4.w > 0) << 3);
+                    np = T - 1 - (cb + __popc(occ & ((1u << c) - 1u)));
+                    if (ncnt[np] > 1) key = 4 * np + qt_quadrant(nrect[np], x, y);
+                } else {
+                    np = T + surv[pos];
+                }
+                keynode[k] = (uint16_t)np;
+            }
+            qt_count(ncc, key);
+        });
+        __syncthreads();
+        { short4* t = rect; rect = nrect; nrect = t; }
+        { int* t = cnt; cnt = ncnt; ncnt = t; }
+        { int* t = cc; cc = ncc; ncc = t; }
         nlive = T + nsurv;
         // ---- termination / phase switch (:674-678, :739-740) ----
         if (tid == 0) {
@@ -1099,15 +1148,26 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
     }
 
     // ---- best key per node: largest response, earliest emission order on ties (:751-767) ----
-    unsigned long long* best = reinterpret_cast<unsigned long long*>(q.cc);
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(ncc);     // the list under construction is free now
     __syncthreads();
     for (int i = tid; i < nlive; i += nt) best[i] = 0ull;
     __syncthreads();
-    for (int k = tid; k < ncand; k += nt) {
-        const uint2 v = cand[k];
-        const unsigned long long key =
-            ((unsigned long long)(v.x >> 24) << 56) | ((unsigned long long)(0xffffffffu - v.y) << 24) | (unsigned)k;
-        atomicMax(&best[keynode[k]], key);
+    for (int base = tid; base < ncand; base += ORBX_QT_MLP * nt) {
+        uint2 v[ORBX_QT_MLP];
+        int pos[ORBX_QT_MLP];
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j) {
+            const int k = base + j * nt;
+            v[j] = k < ncand ? cand[k] : make_uint2(0u, 0u);
+            pos[j] = k < ncand ? (int)keynode[k] : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < ORBX_QT_MLP; ++j)
+            if (pos[j] >= 0) {
+                const unsigned long long key = ((unsigned long long)(v[j].x >> 24) << 56) | ((unsigned long long)(0xffffffffu - v[j].y) << 24) |
+                                               (unsigned)(base + j * nt);
+                atomicMax(&best[pos[j]], key);
+            }
     }
     __syncthreads();
     // ---- kept keypoints in list order + lapping prefix for the two-ended output fill (:1147-1156) ----
@@ -1119,14 +1179,14 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
         const float x = (float)((int)(v & CM) + ORBX_FAST_BORDER);
         const float y = (float)((int)((v >> ORBX_COORD_BITS) & CM) + ORBX_FAST_BORDER);
         const float xs = level != 0 ? __fmul_rn(x, L.sf) : x;
-        q.tmp[i] = (xs >= (float)plan.lap0 && xs <= (float)plan.lap1) ? 1 : 0;
+        tmp[i] = (xs >= (float)plan.lap0 && xs <= (float)plan.lap1) ? 1 : 0;
         OrbxKpRec o;
         o.x = x; o.y = y; o.response = (float)(v >> 24); o.angle = -1.f; o.lap_before = 0; o.src = k;
         rec[i] = o;
     }
     __syncthreads();
-    const int nlap = block_excl_scan(q.tmp, nout, s_scratch);
-    for (int i = tid; i < nout; i += nt) rec[i].lap_before = q.tmp[i];
+    const int nlap = block_excl_scan(tmp, nout, s_scratch);
+    for (int i = tid; i < nout; i += nt) rec[i].lap_before = tmp[i];
     if (tid == 0) ws.level_count[frame * plan.nlevels + level] = make_int2(nout, nlap);
 }
 

@@ -51,6 +51,8 @@ struct OrbxPlan {
     int ncells_total;
     int kp_total;          // sum of kp_cap
     int qt_nc;             // node capacity of the quadtree kernel (max over levels)
+    int qt_sk;             // sort-key slots of the careful phase (qt_nc rounded up to a power of two)
+    long long qt_bytes;    // node storage of one quadtree (orbx_qt_bytes(qt_nc))
     int fast_tp;           // FAST smem tile pitch (bytes)
     int fast_trows;        // FAST smem tile rows
     int fast_qcap;         // FAST smem queue capacity (entries)
@@ -123,6 +125,7 @@ struct OrbxWs {
     int* cand_count;       // [frame][level]
     int2* level_count;     // [frame][level] = {n, n_lapping}
     int* flags;            // one word, bit0: some frame overflowed its candidate workspace
+    uint8_t* qt_scratch;   // NULL: quadtree node tables live in shared memory; else qt_bytes per (frame, level) in HBM
     const int2* xtab;      // resize: {src offset, a0 | a1<<16}
     const int2* ytab;
     const OrbxCell* cells;

@@ -178,15 +178,21 @@ def test_candidate_workspace_regrowth(gpu, oracle):
 
 
 def test_large_feature_counts(gpu, oracle):
-    """nfeatures = 5 * 1500 as the reference demos use (main_orb_extractor.cpp:43) and 14 000; beyond ~14.7 k
-    (more than 3 190 features on one level) the quadtree node table no longer fits shared memory: clean error."""
+    """nfeatures = 5 * 1500 as the reference demos use (main_orb_extractor.cpp:43), and 14 000 / 20 000 / 40 000: the reference has
+    no limit (ORBextractor.cc:439-451, :544-771).  Up to ~2 000 features per level the quadtree node table lives in shared
+    memory, beyond that in a block of HBM per (frame, level); the kernel and the results are the same."""
     img = synth_frame(21, 752, 480)
-    for nf in (7500, 14000):
+    for nf in (7500, 14000, 20000, 40000):
         check_against_oracle(gpu, oracle, img, nf=nf, nl=8, lap=(0, 0), stages=False)
-    ext = gpu.ORBextractor(20000, 1.2, 8, 20, 7)
-    with pytest.raises(gpu.OrbxError) as ei:
-        ext(img, None, (0, 0))
-    assert ei.value.code == -2
+    # a batch through the HBM-resident node tables, and quotas no level can fill (every candidate becomes a keypoint)
+    frames = np.stack([img, synth_frame(22, 752, 480), img[::-1].copy()])
+    ext = gpu.ORBextractor(20000, 1.2, 8, 20, 7, max_batch=3)
+    counts, kps, desc = ext.extract_batch_host(frames, (0, 0))
+    o = oracle.OracleExtractor(20000, 1.2, 8, 20, 7)
+    for f in range(3):
+        oret, okps, odesc = o.extract(frames[f], (0, 0))
+        n = counts[f, 0]
+        assert n == len(okps) and kp_bytes_equal(kps[f, :n], okps) and np.array_equal(desc[f, :n], odesc)
     ext.close()
 
 
