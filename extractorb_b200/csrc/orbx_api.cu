@@ -44,6 +44,7 @@ struct PlanEntry {
     std::vector<OrbxCell> cells;
     std::vector<OrbxFastTile> tiles;
     OrbxFastTile* d_tiles = nullptr;
+    uint8_t* d_slot_level = nullptr;          // level of every kept-keypoint slot (kp_total bytes), k_describe
     size_t ft_smem = 0;
     int2* d_xtab = nullptr;
     int2* d_ytab = nullptr;
@@ -234,7 +235,7 @@ void linear_axis_table(int ssize, int dsize, std::vector<int2>& out) {
 void free_plan(PlanEntry* p) {
     if (!p) return;
     for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_tiles); cudaFree(p->d_blur_tiles);
+    cudaFree(p->d_xtab); cudaFree(p->d_ytab); cudaFree(p->d_cells); cudaFree(p->d_tiles); cudaFree(p->d_slot_level); cudaFree(p->d_blur_tiles);
     delete p;
 }
 
@@ -449,6 +450,13 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     if (!pe->xtab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_xtab, pe->xtab.data(), pe->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->ytab.empty()) ORBX_CUDA(cudaMemcpy(pe->d_ytab, pe->ytab.data(), pe->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!pe->cells.empty()) ORBX_CUDA(cudaMemcpy(pe->d_cells, pe->cells.data(), pe->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint8_t> sl((size_t)std::max(P.kp_total, 1), 0);
+        for (int l = 0; l < L; ++l)
+            for (int i = 0; i < P.lv[l].kp_cap; ++i) sl[(size_t)P.lv[l].kp_off + i] = (uint8_t)l;
+        ORBX_CUDA(cudaMalloc(&pe->d_slot_level, sl.size()));
+        ORBX_CUDA(cudaMemcpy(pe->d_slot_level, sl.data(), sl.size(), cudaMemcpyHostToDevice));
+    }
     ORBX_CUDA(cudaMalloc(&pe->d_tiles, std::max<size_t>(pe->tiles.size(), 1) * sizeof(OrbxFastTile)));
     if (!pe->tiles.empty()) ORBX_CUDA(cudaMemcpy(pe->d_tiles, pe->tiles.data(), pe->tiles.size() * sizeof(OrbxFastTile), cudaMemcpyHostToDevice));
     *out = pe;
@@ -456,7 +464,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
 }
 
 void free_ws_set(OrbxWs& w, bool own_flags) {
-    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps)); cudaFree(w.qt_scratch);
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps)); cudaFree(const_cast<uint8_t*>(w.tmaps_blur)); cudaFree(w.qt_scratch);
     cudaFree(w.kprec); cudaFree(w.cand_count); cudaFree(w.level_count);
     if (own_flags) cudaFree(w.flags);
     memset(&w, 0, sizeof(w));
@@ -471,14 +479,13 @@ void free_workspace(OrbxHandle* h) {
     h->ws_plan = nullptr; h->ws_frames = 0; h->ws2_frames = 0; h->resident_frames = 0; h->cur = nullptr; h->res_set = 0;
 }
 
-// One 3-D tensor map per level over a workspace's pyramid block: (byte column, plane row, frame) with strides (pitch, pyr_stride),
-// box = ft_tp x ft_trows x 1 -- the FAST tile image of k_fast_tiles<true>.  Returns false when TMA cannot describe the plan (box
-// wider than 256 bytes, e.g. cell_size 60) or the driver entry point is missing: the cp.async instance is used instead.
+// TMA tensor maps, one per level, 3-D: (byte column, row, frame) with strides (row pitch, frame stride) and a fixed box.
+//   planes : over a workspace's pyramid block, box = ft_tp x ft_trows -- the FAST tile image of k_fast_tiles<true>
+//   blur   : over its blurred levels, box = 48 x 37 -- the descriptor window of k_describe<true>
+// Returns false when the driver entry point is missing or refuses a map: the cp.async instances are used instead.
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool build_fast_tmaps(PlanEntry* pe, uint8_t* pyr, int frames, std::vector<CUtensorMap>& out) {
-    const OrbxPlan& P = pe->plan;
-    if (P.ft_tp > 256 || P.ft_trows > 256 || P.ntiles_total == 0) return false;
+PFN_encodeTiled tensor_map_encoder() {
     static PFN_encodeTiled encode = nullptr;
     static bool looked = false;
     if (!looked) {
@@ -489,27 +496,41 @@ bool build_fast_tmaps(PlanEntry* pe, uint8_t* pyr, int frames, std::vector<CUten
             encode = (PFN_encodeTiled)fn;
         else
             cudaGetLastError();
+        if (!encode && getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled entry point not found\n");
     }
-    if (!encode) {
-        if (getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled entry point not found\n");
-        return false;
-    }
+    return encode;
+}
+
+bool encode_level_maps(PlanEntry* pe, int frames, bool blur, uint8_t* base, long long frame_stride, int box_w, int box_h,
+                       std::vector<CUtensorMap>& out) {
+    const OrbxPlan& P = pe->plan;
+    PFN_encodeTiled encode = tensor_map_encoder();
+    if (!encode || box_w > 256 || box_h > 256 || (box_w & 15)) return false;
     out.resize((size_t)P.nlevels);
     for (int l = 0; l < P.nlevels; ++l) {
         const OrbxLevel& V = P.lv[l];
-        const cuuint64_t dims[3] = {(cuuint64_t)V.pitch, (cuuint64_t)V.plane_rows, (cuuint64_t)frames};
-        const cuuint64_t strides[2] = {(cuuint64_t)V.pitch, (cuuint64_t)pe->pyr_stride};
-        const cuuint32_t box[3] = {(cuuint32_t)P.ft_tp, (cuuint32_t)P.ft_trows, 1u};
+        const int pitch = blur ? V.blur_pitch : V.pitch, rows = blur ? V.h : V.plane_rows;
+        const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
-        const CUresult cr = encode(&out[(size_t)l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr + V.plane_off, dims, strides, box, estr,
+        const CUresult cr = encode(&out[(size_t)l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base + (blur ? V.blur_off : V.plane_off), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) {
-            if (getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled(level %d) failed with CUresult %d\n", l, (int)cr);
+            if (getenv("ORBX_DEBUG")) fprintf(stderr, "orbx: cuTensorMapEncodeTiled(level %d, %s) failed with CUresult %d\n", l, blur ? "blur" : "planes", (int)cr);
             return false;
         }
     }
     return true;
+}
+
+int upload_maps(OrbxHandle* h, const std::vector<CUtensorMap>& maps, const uint8_t** out) {
+    uint8_t* d = nullptr;
+    ORBX_CUDA(cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)));
+    ORBX_CUDA(cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    *out = d;
+    return ORBX_OK;
 }
 
 int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* shared_flags) {
@@ -533,16 +554,19 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
         ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
         ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
     }
-    w.tmaps = nullptr;
+    w.tmaps = nullptr; w.tmaps_blur = nullptr;
     if (h->fast_tma) {
         std::vector<CUtensorMap> maps;
-        if (build_fast_tmaps(pe, w.pyr, frames, maps)) {
-            uint8_t* d = nullptr;
-            ORBX_CUDA(cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)));
-            ORBX_CUDA(cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-            w.tmaps = d;
+        if (P.ntiles_total > 0 && encode_level_maps(pe, frames, false, w.pyr, pe->pyr_stride, P.ft_tp, P.ft_trows, maps)) {
+            const int ru = upload_maps(h, maps, &w.tmaps);
+            if (ru != ORBX_OK) return ru;
+        }
+        if (encode_level_maps(pe, frames, true, w.blur, pe->blur_stride, ORBX_DESC_PP, 37, maps)) {
+            const int ru = upload_maps(h, maps, &w.tmaps_blur);
+            if (ru != ORBX_OK) return ru;
         }
     }
+    w.slot_level = pe->d_slot_level;
     w.pyr_stride = pe->pyr_stride; w.blur_stride = pe->blur_stride; w.cand_stride = pe->cand_stride;
     w.kp_stride = P.kp_total;
     w.xtab = pe->d_xtab; w.ytab = pe->d_ytab; w.cells = pe->d_cells; w.tiles = pe->d_tiles;
@@ -715,8 +739,12 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
     if (per_level) {
         for (int l = 0; l < P.nlevels; ++l) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_lvl_done[l], 0));
         ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-        k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
-            P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        if (ws.tmaps_blur)
+            k_describe<true><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+                P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        else
+            k_describe<false><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+                P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         ++launches;
     } else if (stages & STAGES_KEYPOINTS) {
         ORBX_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)P.nlevels * nf * sizeof(int), st));
@@ -751,8 +779,12 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
         nvtx_stage("orbx:describe");
-        k_describe<<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
-            P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        if (ws.tmaps_blur)
+            k_describe<true><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+                P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
+        else
+            k_describe<false><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+                P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[5], st));
     } else if (se) {
@@ -2001,6 +2033,6 @@ int orbx_synchronize(OrbxHandle* h) {
 
 void* orbx_get_stream(const OrbxHandle* h) { return h ? (void*)h->stream : nullptr; }
 
-int orbx_uses_tma(const OrbxHandle* h) { return h && h->ws_plan && h->ws.tmaps ? 1 : 0; }
+int orbx_uses_tma(const OrbxHandle* h) { return h && h->ws_plan && h->ws.tmaps && h->ws.tmaps_blur ? 1 : 0; }
 
 }  // extern "C"

@@ -26,6 +26,27 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p >= len ? 2 * (len - 1) - p : p;
 }
 
+// TMA + mbarrier helpers (sm_90+ PTX; SASS: UTMALDG / SYNCS).  One thread arms the barrier with the byte count of the box and
+// issues the bulk tensor copy; the copy engine lands the box in shared memory and completes the barrier's transaction count.
+__device__ __forceinline__ void orbx_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void orbx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void orbx_tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ bool orbx_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+
 // =================================================================================================
 // K1  ComputePyramid.
 // =================================================================================================
@@ -574,26 +595,6 @@ __device__ __forceinline__ unsigned ft_queue_pair(unsigned qa, unsigned mk, int 
     ORBX_FT_PUSH(0x00000008u, 4) ORBX_FT_PUSH(0x00000800u, 5) ORBX_FT_PUSH(0x00080000u, 6) ORBX_FT_PUSH(0x08000000u, 7)
 #undef ORBX_FT_PUSH
     return qa;
-}
-
-// TMA + mbarrier helpers (sm_90+ PTX; SASS: UTMALDG / SYNCS).  One thread arms the barrier with the byte count of the box and
-// issues the bulk tensor copy; the copy engine lands the box in shared memory and completes the barrier's transaction count.
-__device__ __forceinline__ void orbx_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void orbx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void orbx_tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ bool orbx_mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
 }
 
 // TMA: the tile image arrives as ONE bulk tensor copy (box = ft_tp bytes x ft_trows rows of the level's plane, described by
@@ -1390,19 +1391,24 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned a, int b, int c) {
 #define ORBX_RND_MAGIC 12582912.0f
 #define ORBX_RND_BIAS 0x4B400000
 
+// TMA: the 37-row window of the blurred level arrives as one bulk tensor copy per keypoint (box 64 B x 37 rows from the level's
+// tensor map over the blur buffer, one mbarrier per warp) instead of 13 rounds of 4-byte cp.async with their index arithmetic.
+// The box starts at a 16-byte aligned column (a box starting at an arbitrary byte never completed on the B200: trap), so it is
+// 64 bytes wide: up to 15 bytes of alignment slack + the 37 columns.
+#define ORBX_DESC_PP 64        // patch row pitch in shared memory = TMA box width
+template <bool TMA>
 __global__ void __launch_bounds__(ORBX_DESC_WARPS * 32, 8)
 k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFloatConsts fc,
            void* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
            int cap_per_frame, int32_t* __restrict__ counts, int frame_out0) {
-    __shared__ __align__(16) uint8_t s_patch[ORBX_DESC_WARPS][37 * 44 + 4];
+    __shared__ __align__(128) uint8_t s_patch[ORBX_DESC_WARPS][37 * ORBX_DESC_PP + 64];     // 2432 B per warp: 128-byte aligned slots
+    __shared__ __align__(8) unsigned long long s_bar[ORBX_DESC_WARPS];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * ORBX_DESC_WARPS + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
     if (slot >= plan.kp_total) return;
-    // level of this slot from the plan (no memory access), record load issued together with the level counts
-    int level = 0;
-#pragma unroll
-    for (int l = 1; l < ORBX_MAX_LEVELS; ++l) level += (l < plan.nlevels && slot >= plan.lv[l].kp_off) ? 1 : 0;
+    // level of this slot: one byte from the plan's slot table
+    const int level = __ldg(ws.slot_level + slot);
     const OrbxLevel& L = plan.lv[level];
     const int idx = slot - L.kp_off;
     OrbxKpRec* recp = ws.kprec + (long long)frame * ws.kp_stride + slot;
@@ -1430,24 +1436,34 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     if (idx >= n_level) return;
     const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
-    // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory with aligned
-    // 32-bit cp.async copies, issued first so that they overlap the moment computation below.
+    // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory, issued first so that the copy
+    // overlaps the moment computation below: one TMA box, or aligned 32-bit cp.async copies.
     const int bp = L.blur_pitch;
-    const int bx0 = cx - 18, o0 = bx0 & 3;
-    const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
-                                                              (long long)(cy - 18) * bp + (bx0 - o0));
+    const int bx0 = cx - 18, o0 = TMA ? (bx0 & 15) : (bx0 & 3);
     uint8_t* patch = s_patch[threadIdx.x >> 5];
-    const int bpw = bp >> 2;
-#pragma unroll
-    for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
-        const int i = it * 32 + lane;
-        if (i < 37 * 11) {
-            const int row = (i * 373) >> 12;               // i / 11 for i < 407
-            const int wd = i - row * 11;
-            __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(patch) + i, b32 + row * bpw + wd, 4);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]);
+    if (TMA) {
+        if (lane == 0) {
+            orbx_mbar_init(bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            orbx_mbar_expect_tx(bar, 37 * ORBX_DESC_PP);
+            orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(patch), ws.tmaps_blur + 128 * level, bar, bx0 - o0, cy - 18, frame);
         }
+    } else {
+        const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
+                                                                  (long long)(cy - 18) * bp + (bx0 - o0));
+        const int bpw = bp >> 2;
+#pragma unroll
+        for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
+            const int i = it * 32 + lane;
+            if (i < 37 * 11) {
+                const int row = (i * 373) >> 12;               // i / 11 for i < 407
+                const int wd = i - row * 11;
+                __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(patch) + row * (ORBX_DESC_PP / 4) + wd, b32 + row * bpw + wd, 4);
+            }
+        }
+        __pipeline_commit();
     }
-    __pipeline_commit();
 
     // ---- IC_Angle on the un-blurred level: 31 rows x 9 aligned words, IDP.4A against per-alignment
     // weight words (u inside the circle, else 0) and mask words (1 inside the circle) ----
@@ -1484,10 +1500,18 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     // host, tools/check_sincosf.c), so the sample coordinates -- and the descriptors -- are bit-identical, not just close.
     float a, b;
     orbx_glibc_sincosf(rad, &b, &a);
-    __pipeline_wait_prior(0);
+    if (TMA) {
+        __syncwarp();                                           // lane 0 has initialised the barrier and issued the copy
+        unsigned spins = 0;
+        while (!orbx_mbar_try_wait(bar, 0)) {
+            if (++spins > (1u << 18)) __trap();                 // a copy that never lands must fail loudly, not hang the device
+        }
+    } else {
+        __pipeline_wait_prior(0);
+    }
     __syncwarp();
-    // sample index = (round(r)+18)*44 + round(c)+18+o0; the rounding bias of both terms is folded into K
-    const int K = (int)((unsigned)(18 - ORBX_RND_BIAS) * 44u + (unsigned)(18 + o0 - ORBX_RND_BIAS));   // wraps, like the index arithmetic
+    // sample index = (round(r)+18)*pitch + round(c)+18+o0; the rounding bias of both terms is folded into K
+    const int K = (int)((unsigned)(18 - ORBX_RND_BIAS) * (unsigned)ORBX_DESC_PP + (unsigned)(18 + o0 - ORBX_RND_BIAS));   // wraps, like the index arithmetic
     const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
     int val = 0;
 #pragma unroll
@@ -1497,8 +1521,8 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
         const float c0 = __fadd_rn(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)), ORBX_RND_MAGIC);
         const float r1 = __fadd_rn(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)), ORBX_RND_MAGIC);
         const float c1 = __fadd_rn(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)), ORBX_RND_MAGIC);
-        const int t0 = patch[__float_as_int(r0) * 44 + __float_as_int(c0) + K];
-        const int t1 = patch[__float_as_int(r1) * 44 + __float_as_int(c1) + K];
+        const int t0 = patch[__float_as_int(r0) * ORBX_DESC_PP + __float_as_int(c0) + K];
+        const int t1 = patch[__float_as_int(r1) * ORBX_DESC_PP + __float_as_int(c1) + K];
         val |= (t0 < t1) << k;
     }
 
