@@ -56,6 +56,7 @@ struct PlanEntry {
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
+    int rs_launch_pitch[ORBX_MAX_LEVELS] = {0};  // staging pitch actually used at launch (ORBX_RS_PITCH for the specialised instance)
     // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
     struct GraphKey {
         const void* imgs; long long rs, fs; int nf, lap0, lap1; void* kps; void* desc; int cap; void* counts; int fo, stages;
@@ -287,6 +288,11 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
             }
             pe->rs_rows[l] = rows;
+            {
+                const bool area_l = pe->xtab[V.xtab_off].y == -1;
+                const int pp = (int)align_up(cols + 15 + 15, 16);
+                pe->rs_launch_pitch[l] = (!area_l && pp <= ORBX_RS_PITCH) ? ORBX_RS_PITCH : pp;
+            }
             pe->rs_pitch[l] = (int)align_up(cols + 15 + 15, 16);     // 16-byte aligned window start + whole 16-byte vectors
         }
         // FAST cell grid, :781-814
@@ -464,7 +470,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
 }
 
 void free_ws_set(OrbxWs& w, bool own_flags) {
-    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps)); cudaFree(const_cast<uint8_t*>(w.tmaps_blur)); cudaFree(w.qt_scratch);
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.keynode); cudaFree(const_cast<uint8_t*>(w.tmaps)); cudaFree(const_cast<uint8_t*>(w.tmaps_blur)); cudaFree(const_cast<uint8_t*>(w.tmaps_b7)); cudaFree(const_cast<uint8_t*>(w.tmaps_rs)); cudaFree(w.qt_scratch);
     cudaFree(w.kprec); cudaFree(w.cand_count); cudaFree(w.level_count);
     if (own_flags) cudaFree(w.flags);
     memset(&w, 0, sizeof(w));
@@ -501,14 +507,19 @@ PFN_encodeTiled tensor_map_encoder() {
     return encode;
 }
 
-bool encode_level_maps(PlanEntry* pe, int frames, bool blur, uint8_t* base, long long frame_stride, int box_w, int box_h,
+// box_w / box_h <= 0: per level, the resize kernel's staging window (entry l describes the plane of level l - 1)
+bool encode_level_maps(PlanEntry* pe, int frames, bool blur, uint8_t* base, long long frame_stride, int box_w_all, int box_h_all,
                        std::vector<CUtensorMap>& out) {
     const OrbxPlan& P = pe->plan;
     PFN_encodeTiled encode = tensor_map_encoder();
-    if (!encode || box_w > 256 || box_h > 256 || (box_w & 15)) return false;
+    if (!encode) return false;
+    const bool resize = box_w_all <= 0;
     out.resize((size_t)P.nlevels);
-    for (int l = 0; l < P.nlevels; ++l) {
-        const OrbxLevel& V = P.lv[l];
+    memset(out.data(), 0, out.size() * sizeof(CUtensorMap));
+    for (int l = resize ? 1 : 0; l < P.nlevels; ++l) {
+        const OrbxLevel& V = P.lv[resize ? l - 1 : l];
+        const int box_w = resize ? pe->rs_launch_pitch[l] : box_w_all, box_h = resize ? pe->rs_rows[l] : box_h_all;
+        if (box_w > 256 || box_h > 256 || (box_w & 15) || box_w < 16 || box_h < 1) return false;
         const int pitch = blur ? V.blur_pitch : V.pitch, rows = blur ? V.h : V.plane_rows;
         const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)frames};
         const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
@@ -554,7 +565,7 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
         ORBX_CUDA(cudaMalloc(&w.flags, sizeof(int)));
         ORBX_CUDA(cudaMemset(w.flags, 0, sizeof(int)));
     }
-    w.tmaps = nullptr; w.tmaps_blur = nullptr;
+    w.tmaps = nullptr; w.tmaps_blur = nullptr; w.tmaps_b7 = nullptr; w.tmaps_rs = nullptr;
     if (h->fast_tma) {
         std::vector<CUtensorMap> maps;
         if (P.ntiles_total > 0 && encode_level_maps(pe, frames, false, w.pyr, pe->pyr_stride, P.ft_tp, P.ft_trows, maps)) {
@@ -563,6 +574,14 @@ int alloc_ws_set(OrbxHandle* h, PlanEntry* pe, int frames, OrbxWs& w, int* share
         }
         if (encode_level_maps(pe, frames, true, w.blur, pe->blur_stride, ORBX_DESC_PP, 37, maps)) {
             const int ru = upload_maps(h, maps, &w.tmaps_blur);
+            if (ru != ORBX_OK) return ru;
+        }
+        if (encode_level_maps(pe, frames, false, w.pyr, pe->pyr_stride, ORBX_BLUR_TW + 32, ORBX_BLUR_TH + 6, maps)) {
+            const int ru = upload_maps(h, maps, &w.tmaps_b7);
+            if (ru != ORBX_OK) return ru;
+        }
+        if (P.nlevels > 1 && encode_level_maps(pe, frames, false, w.pyr, pe->pyr_stride, 0, 0, maps)) {
+            const int ru = upload_maps(h, maps, &w.tmaps_rs);
             if (ru != ORBX_OK) return ru;
         }
     }
@@ -702,8 +721,11 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
                 else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
                 else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             } else {
+                const bool tma = ws.tmaps_rs != nullptr && !area;
                 if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (fixed && tma) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
                 else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                else if (tma) k_pyr_resize<false, 0, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
                 else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
             }
             ++launches;
@@ -728,7 +750,8 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         }
         h->borders_valid[set] = want_border;
         if (fork) {
-            k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, sb>>>(P, ws, 0);
+            if (ws.tmaps_b7) k_blur7<true><<<dim3(pe->blur_tiles, nf), 256, 0, sb>>>(P, ws, 0);
+            else k_blur7<false><<<dim3(pe->blur_tiles, nf), 256, 0, sb>>>(P, ws, 0);
             ++launches;
             ORBX_CUDA(cudaEventRecord(h->ev_join, sb));
         }
@@ -774,7 +797,8 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         if (forked) {
             ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         } else {
-            k_blur7<<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws, 1);
+            if (ws.tmaps_b7) k_blur7<true><<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws, 1);
+            else k_blur7<false><<<dim3(pe->blur_tiles, nf), 256, 0, st>>>(P, ws, 1);
             ++launches;
         }
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
@@ -891,6 +915,8 @@ int set_kernel_attrs_device(OrbxHandle* h) {
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_BIG>, optin));
     ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, 0, ORBX_RS_TH>, optin));
     ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH, true>, optin));
+    ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, 0, ORBX_RS_TH, true>, optin));
     ORBX_CUDA(raise_smem_limit(k_pyr_resize<true, 0, ORBX_RS_TH>, optin));
     ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, 0, ORBX_RS_TH_LAT>, optin));
     ORBX_CUDA(raise_smem_limit(k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT>, optin));
@@ -2033,6 +2059,6 @@ int orbx_synchronize(OrbxHandle* h) {
 
 void* orbx_get_stream(const OrbxHandle* h) { return h ? (void*)h->stream : nullptr; }
 
-int orbx_uses_tma(const OrbxHandle* h) { return h && h->ws_plan && h->ws.tmaps && h->ws.tmaps_blur ? 1 : 0; }
+int orbx_uses_tma(const OrbxHandle* h) { return h && h->ws_plan && h->ws.tmaps && h->ws.tmaps_blur && h->ws.tmaps_b7 ? 1 : 0; }
 
 }  // extern "C"

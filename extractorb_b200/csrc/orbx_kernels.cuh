@@ -133,10 +133,13 @@ __device__ __forceinline__ void border_right_word(const uint32_t* __restrict__ s
     drow[wx] = word;
 }
 
-template <bool AREA, int PITCH, int TH>
+// TMA: the source window (box = staging pitch x src_rows_max bytes of the previous level's plane, ws.tmaps_rs[level]) arrives as
+// one bulk tensor copy instead of ~1000 16-byte cp.async.
+template <bool AREA, int PITCH, int TH, bool TMA = false>
 __global__ void __launch_bounds__(256)
 k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
-    extern __shared__ __align__(16) uint8_t smem_rs[];
+    extern __shared__ __align__(128) uint8_t smem_rs[];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int src_pitch_s = PITCH ? PITCH : src_pitch_rt;
     const OrbxLevel& L = plan.lv[level];
     const OrbxLevel& S = plan.lv[level - 1];
@@ -158,15 +161,25 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     uint8_t* s_src = smem_rs;                                           // [src_rows_max][src_pitch_s]
     uint8_t* s_hb = smem_rs + (size_t)src_rows_max * src_pitch_s;       // [src_rows_max][TW] uint16
     int4* s_yt = reinterpret_cast<int4*>(s_hb + (size_t)src_rows_max * ORBX_RS_TW * 2);   // [TH] row descriptors
-    // ---- stage (16-byte cp.async; plane rows are 64-byte aligned): 16 or 32 lanes per source row ----
+    // ---- stage: one TMA box, or 16-byte cp.async (plane rows are 64-byte aligned), 16 or 32 lanes per source row ----
     {
-        const uint8_t* g = splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al);
-        const int sh = nvec <= 16 ? 4 : 5;
-        const int v0 = tid & ((1 << sh) - 1), rstep = 256 >> sh;
-        for (int v = v0; v < nvec; v += 1 << sh)
-            for (int r = tid >> sh; r < nrows; r += rstep)
-                __pipeline_memcpy_async(s_src + r * src_pitch_s + 16 * v, g + (long long)r * S.pitch + 16 * v, 16);
-        __pipeline_commit();
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (TMA) {
+            if (tid == 0) {
+                orbx_mbar_init(bar, 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                orbx_mbar_expect_tx(bar, (uint32_t)(src_rows_max * src_pitch_s));
+                orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(s_src), ws.tmaps_rs + 128 * level, bar, gcol - al, ORBX_EDGE + sy_lo, frame);
+            }
+        } else {
+            const uint8_t* g = splane + (long long)(ORBX_EDGE + sy_lo) * S.pitch + (gcol - al);
+            const int sh = nvec <= 16 ? 4 : 5;
+            const int v0 = tid & ((1 << sh) - 1), rstep = 256 >> sh;
+            for (int v = v0; v < nvec; v += 1 << sh)
+                for (int r = tid >> sh; r < nrows; r += rstep)
+                    __pipeline_memcpy_async(s_src + r * src_pitch_s + 16 * v, g + (long long)r * S.pitch + 16 * v, 16);
+            __pipeline_commit();
+        }
         // destination-row descriptors: byte offsets of the two source rows inside s_h, vertical coefficients << 16
         if (tid < th) {
             const int2 yt = __ldg(&ytab[y0 + tid]);
@@ -174,7 +187,15 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
             s_yt[tid] = make_int4(r0 * (ORBX_RS_TW * 2), r1 * (ORBX_RS_TW * 2), (int)((unsigned)(yt.y & 0xffff) << 16),
                                   (int)((unsigned)(yt.y >> 16) << 16));
         }
-        __pipeline_wait_prior(0);
+        if (TMA) {
+            __syncthreads();                               // the barrier is initialised before anybody polls it
+            unsigned spins = 0;
+            while (!orbx_mbar_try_wait(bar, 0)) {
+                if (++spins > (1u << 18)) __trap();
+            }
+        } else {
+            __pipeline_wait_prior(0);
+        }
     }
     __syncthreads();
     // ---- horizontal pass: thread owns one destination column, walks the staged rows.  Full tiles: two row
@@ -1202,13 +1223,16 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
 // Horizontal taps via IDP.4A on byte-aligned windows (funnel shifts of the staged words), vertical taps via
 // IDP.2A on 16-bit horizontal sums stored as row pairs (rows 2k, 2k+1 share one 32-bit word per column).
 // blockIdx.x indexes a host-built tile table (level | tile_x << 8 | tile_y << 20).
+// TMA: the 160 x 70 byte source window arrives as one bulk tensor copy (ws.tmaps_b7, the level's plane) instead of 700 cp.async.
+template <bool TMA>
 __global__ void __launch_bounds__(256)
 k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) {
     constexpr int SROWS = ORBX_BLUR_TH + 6;          // 70 staged rows = 35 row pairs
     constexpr int SPB = ORBX_BLUR_TW + 32;           // staged bytes per row: columns x0-16 .. x0+143 (16-byte chunks)
     constexpr int SW = SPB / 4;
-    __shared__ __align__(16) uint32_t s_src[SROWS * SW];
+    __shared__ __align__(128) uint32_t s_src[SROWS * SW];
     __shared__ __align__(16) uint32_t s_h2[(SROWS / 2) * ORBX_BLUR_TW];
+    __shared__ __align__(8) unsigned long long s_bar;
     const uint32_t tdesc = __ldg(ws.blur_tiles + blockIdx.x);
     const int level = tdesc & 0xff;
     const OrbxLevel& L = plan.lv[level];
@@ -1219,7 +1243,35 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
     const int x0 = ((tdesc >> 8) & 0xfff) * ORBX_BLUR_TW, y0 = (tdesc >> 20) * ORBX_BLUR_TH;
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int tid = threadIdx.x;
-    {
+    if (TMA) {
+        // the box holds plane rows 19 + y0 - 3 ..: halo rows above / below the level are the (possibly unwritten) border, so the
+        // tiles on the top / bottom edge mirror their three halo rows in shared memory, like the halo columns below
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (tid == 0) {
+            orbx_mbar_init(bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            orbx_mbar_expect_tx(bar, SROWS * SPB);
+            orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(s_src), ws.tmaps_b7 + 128 * level, bar, ORBX_PADL + x0 - 16, ORBX_EDGE + y0 - 3, frame);
+        }
+        __syncthreads();                                   // the barrier is initialised before anybody polls it
+        unsigned spins = 0;
+        while (!orbx_mbar_try_wait(bar, 0)) {
+            if (++spins > (1u << 18)) __trap();
+        }
+        const bool top = y0 == 0, bottom = L.h <= y0 + ORBX_BLUR_TH + 2;
+        if (top || bottom) {
+            // staged row r holds level row y0 - 3 + r
+            for (int i = tid; i < 6 * SW; i += 256) {
+                const int k = i / SW, wd = i - k * SW;     // k = 0..2: rows above the level, 3..5: rows below it
+                if (k < 3) {
+                    if (top) s_src[(2 - k) * SW + wd] = s_src[(4 + k) * SW + wd];          // level row -(k+1) <- row k+1
+                } else if (bottom) {
+                    const int e = L.h - y0 + 3 + (k - 3);  // staged index of level row h + (k-3)
+                    if (e < SROWS) s_src[e * SW + wd] = s_src[(e - 2 - 2 * (k - 3)) * SW + wd];   // level row h+j <- row h-2-j
+                }
+            }
+        }
+    } else {
         // BORDER_REFLECT_101 of the borderless clone the reference blurs (:1126-1127), without reading the plane's border (it may
         // not have been written, see k_pyr_border): halo rows come from the mirrored level row, the 3 halo columns of the tiles
         // on the left / right edge are mirrored in shared memory below.

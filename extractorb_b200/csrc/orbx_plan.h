@@ -131,7 +131,9 @@ struct OrbxWs {
     const OrbxCell* cells;
     const OrbxFastTile* tiles;
     const uint8_t* tmaps;     // one 128-byte CUtensorMap per level over this workspace's planes (k_fast_tiles<true>), or NULL
-    const uint8_t* tmaps_blur; // ... over its blurred levels, box 48 x 37 (k_describe<true>), or NULL
+    const uint8_t* tmaps_blur; // ... over its blurred levels, box 64 x 37 (k_describe<true>), or NULL
+    const uint8_t* tmaps_b7;   // ... over its planes, box 160 x 70 (k_blur7<true>), or NULL
+    const uint8_t* tmaps_rs;   // ... entry l over the plane of level l-1, box = staging pitch x rows of k_pyr_resize<.., true>, or NULL
     const uint8_t* slot_level; // level of every kept-keypoint slot of a frame (kp_total bytes)
     const float* pattern_f;   // rBRIEF tests as floats, layout [bit k][descriptor byte][x0, y0, x1, y1]
     const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
