@@ -345,10 +345,14 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = ext.launch_count() - launches0
-    ms_max = allmax(ms)
-    value = F * world * args.steps / (ms_max * 1e-3)
     counts = d_counts.cpu().numpy()
-    kp_sum = allsum(float(counts[:, 0].sum()))           # statistics only: frames need no data collective
+    # whole-job statistics: SUM of frames / keypoints, MAX of the elapsed time over ranks (extractorb_b200/sharding.py; NCCL here, gloo in
+    # the CPU tests) -- the only collectives of the job, frames need no data exchange
+    from extractorb_b200 import sharding
+    stats = sharding.reduce_stats(frames=F * args.steps, keypoints=int(counts[:, 0].sum()), elapsed_ms=ms, device="cuda")
+    ms_max = stats["elapsed_ms_max"]
+    value = stats["frames"] / (ms_max * 1e-3)
+    kp_sum = float(stats["keypoints"])
     ncand = sum(len(ext.level_candidates(l, frame=0)[0]) for l in range(NLEVELS))   # of one frame of the workload
 
     # Per-stage CUDA-event times (and the dominant kernel's launch duration for the roofline) come from a second,

@@ -1313,6 +1313,26 @@ int check_batch_args(OrbxHandle* h, const BatchArgs& a) {
 
 extern "C" {
 
+// The launch-group sizes a host-buffer call of n_frames frames is cut into (device-free: the same next_group the pipeline uses,
+// consumers taking turns), for tests and for callers that size their own staging.
+int orbx_plan_groups(int n_frames, int max_batch, int consumers, int ramp, int32_t* sizes, int capacity) {
+    if (n_frames < 0 || max_batch < 1 || consumers < 1) return ORBX_ERR_BAD_ARGUMENT;
+    FramePool pool;
+    pool.n_frames = n_frames;
+    pool.consumers = consumers;
+    const int group = std::min(max_batch, std::max(n_frames, 1));
+    std::vector<int> gi((size_t)consumers, 0);
+    int n = 0;
+    for (int c = 0;; c = (c + 1) % consumers) {
+        int f0 = 0;
+        const int nf = next_group(pool, group, gi[(size_t)c]++, ramp != 0, &f0);
+        if (nf == 0) break;
+        if (sizes && n < capacity) sizes[n] = nf;
+        ++n;
+    }
+    return n;
+}
+
 int orbx_extract_batch(OrbxHandle* h, const uint8_t* images, int in_mem, int n_frames, int width, int height,
                        size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps, uint8_t* desc,
                        int cap_per_frame, int32_t* counts, int out_mem, void* stream) {

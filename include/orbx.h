@@ -127,6 +127,11 @@ ORBX_API int orbx_extract_batch_multi(OrbxHandle* const* handles, int n_handles,
                              int height, size_t row_stride, size_t frame_stride, int lap0, int lap1, OrbxKeyPoint* kps,
                              uint8_t* desc, int cap_per_frame, int32_t* counts, int32_t* frames_per_handle);
 
+/* The launch-group sizes a host-buffer call of n_frames frames is cut into (sizes[0..return value), at most `capacity` written):
+ * groups ramp up at the start and down at the end of a call, never above max_batch.  `consumers` > 1: the handles of
+ * orbx_extract_batch_multi taking turns.  Needs no device. */
+ORBX_API int orbx_plan_groups(int n_frames, int max_batch, int consumers, int ramp, int32_t* sizes, int capacity);
+
 /* Stage-wise entry points mirroring the reference's public methods (inc/ORBextractor.h:89-92), which the
  * demos call directly (src/orb_extractor/main_orb_extractor.cpp:44-46). */
 ORBX_API int orbx_compute_pyramid(OrbxHandle* h, const uint8_t* image, int width, int height, size_t stride);
