@@ -380,6 +380,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 pe->tiles.push_back(T);
                 ft_maxtw = std::max(ft_maxtw, (int)T.tw); ft_maxth = std::max(ft_maxth, (int)T.th);
                 ft_qcap = std::max(ft_qcap, (T.tw - 6) * (T.th - 6));
+                if (npairs > 32) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "internal: more than 32 pairs per FAST tile row"); }
                 // strict 3x3 maxima inside a cell: at most one per 2x2 block of its interior
                 ft_scap = std::max(ft_scap, nc * ((V.wCell + 1) / 2) * ((T.th - 6 + 1) / 2));
                 j0 += nc;
@@ -1034,7 +1035,10 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
         std::vector<float> pf(1024);
         // device layout [k][lane][4]: test t = 8*lane + k (descriptor byte `lane`, bit k) so that a warp's loads coalesce
         for (int t = 0; t < 256; ++t)
-            for (int c = 0; c < 4; ++c) pf[(size_t)((t & 7) * 32 + (t >> 3)) * 4 + c] = (float)kPatternHost[4 * t + c];
+            for (int c = 0; c < 4; ++c) {
+                const int slot = c == 1 ? 2 : (c == 2 ? 1 : c);      // stored as (x0, x1, y0, y1): the two points side by side for the packed FP32 ops
+                pf[(size_t)((t & 7) * 32 + (t >> 3)) * 4 + slot] = (float)kPatternHost[4 * t + c];
+            }
         // IC_Angle weight words: byte k of the aligned row window is patch column u = k - al - 15 (:82-97)
         std::vector<int2> aw((size_t)4 * 31 * ORBX_ANGLE_WORDS);
         for (int al = 0; al < 4; ++al)
@@ -1185,7 +1189,11 @@ int extract_pass(OrbxHandle* h, FramePool& pool, const BatchArgs& a, cudaStream_
     PlanEntry* pe = nullptr;
     int rc = get_plan(h, width, height, &pe);
     if (rc != ORBX_OK) return rc;
-    const int group = std::min(h->prm.max_batch, n_frames);
+    // Host-buffer pipelines of many groups run with launch groups of at most 128 frames: the finer grain shortens the fill and
+    // drain of the three-stream pipeline (166.6 k vs 161.1 k frames/s end to end at 4096 frames per call, profiles/r02_e2e_knobs.txt),
+    // while device-resident calls keep max_batch (larger groups are faster there).
+    const bool host_side = a.in_mem == ORBX_MEM_HOST || a.out_mem == ORBX_MEM_HOST;
+    const int group = std::min(host_side && n_frames >= 1024 ? std::min(h->prm.max_batch, 128) : h->prm.max_batch, n_frames);
     const bool multi_group = n_frames > group || pool.consumers > 1;
     // Consecutive launch groups alternate between two workspace sets and two compute streams, so that the
     // latency-bound kernels and the tail of every kernel of one group overlap the next group's kernels.

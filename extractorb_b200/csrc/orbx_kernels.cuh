@@ -1387,6 +1387,21 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbxFloa
     return a;
 }
 
+// Blackwell's packed FP32 multiply (FMUL2: two IEEE round-to-nearest products per instruction), spelled as PTX with the explicit .rn
+// qualifier.  Only the products are packed: a packed mul feeding a packed add is fused by ptxas into FFMA2 -- one rounding instead of
+// two, which would change descriptor bits -- even with .rn on both and -fmad=false (the __fmul2_rn / __fadd2_rn intrinsics of
+// sm_100_rt.h behave the same); a scalar add of the two halves is left alone.
+__device__ __forceinline__ float2 orbx_mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 orbx_add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 #define ORBX_DESC_WARPS 8
 #define ORBX_ANGLE_WORDS 9   // 31 patch columns + up to 3 bytes of alignment slack = 9 aligned words per row
 
@@ -1565,16 +1580,19 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     // sample index = (round(r)+18)*pitch + round(c)+18+o0; the rounding bias of both terms is folded into K
     const int K = (int)((unsigned)(18 - ORBX_RND_BIAS) * (unsigned)ORBX_DESC_PP + (unsigned)(18 + o0 - ORBX_RND_BIAS));   // wraps, like the index arithmetic
     const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
+    // Both points of a test share Blackwell's packed FP32 instructions: FMUL2 for the four products, scalar adds (see orbx_mul2),
+    // FADD2 for the rounding constant -- the same bits as sixteen scalar operations in ten.  x*a - y*b is x*a + y*(-b): negation is exact.
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b), nb = make_float2(-b, -b), mm = make_float2(ORBX_RND_MAGIC, ORBX_RND_MAGIC);
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float4 t = __ldg(pat + k * 32);   // test 8*lane + k: x0, y0, x1, y1
-        const float r0 = __fadd_rn(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)), ORBX_RND_MAGIC);
-        const float c0 = __fadd_rn(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)), ORBX_RND_MAGIC);
-        const float r1 = __fadd_rn(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)), ORBX_RND_MAGIC);
-        const float c1 = __fadd_rn(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)), ORBX_RND_MAGIC);
-        const int t0 = patch[__float_as_int(r0) * ORBX_DESC_PP + __float_as_int(c0) + K];
-        const int t1 = patch[__float_as_int(r1) * ORBX_DESC_PP + __float_as_int(c1) + K];
+        const float4 t = __ldg(pat + k * 32);   // test 8*lane + k: x0, x1, y0, y1
+        const float2 px = make_float2(t.x, t.y), py = make_float2(t.z, t.w);
+        const float2 xb = orbx_mul2(px, bb), ya = orbx_mul2(py, aa), xa = orbx_mul2(px, aa), yb = orbx_mul2(py, nb);
+        const float2 r = orbx_add2(make_float2(__fadd_rn(xb.x, ya.x), __fadd_rn(xb.y, ya.y)), mm);
+        const float2 c = orbx_add2(make_float2(__fadd_rn(xa.x, yb.x), __fadd_rn(xa.y, yb.y)), mm);
+        const int t0 = patch[__float_as_int(r.x) * ORBX_DESC_PP + __float_as_int(c.x) + K];
+        const int t1 = patch[__float_as_int(r.y) * ORBX_DESC_PP + __float_as_int(c.y) + K];
         val |= (t0 < t1) << k;
     }
 

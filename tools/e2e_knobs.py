@@ -23,7 +23,7 @@ def child(group, wc, pin_cpu):
     import bench
     import extractorb_b200 as ex
     if pin_cpu >= 0:
-        os.sched_setaffinity(0, {pin_cpu})          # before the pinned allocations: first touch on this core's node
+        os.sched_setaffinity(0, set(range(pin_cpu, pin_cpu + 4)))   # before the pinned allocations: first touch on these cores' node
     F, W, H = 4096, bench.W, bench.H
     frames = bench.make_frames(F, seed=0)
     L = ex.load_library()
@@ -61,10 +61,15 @@ if __name__ == "__main__":
         sys.exit(0)
     settings = [("default (4 slots, ramp, group 256)", {}, 256, 0, -1), ("3 slots", {"ORBX_SLOTS": "3"}, 256, 0, -1), ("2 slots", {"ORBX_SLOTS": "2"}, 256, 0, -1),
                 ("no ramp", {"ORBX_RAMP": "0"}, 256, 0, -1), ("group 128", {}, 128, 0, -1), ("group 512", {}, 512, 0, -1),
-                ("write-combined input", {}, 256, 1, -1), ("pinned to one core", {}, 256, 0, 2)]
+                ("write-combined input", {}, 256, 1, -1), ("pinned to cores 4-7", {}, 256, 0, 4)]
     for name, env, group, wc, cpu in settings:
         e = dict(os.environ); e.update(env)
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(group), str(wc), str(cpu)], env=e, capture_output=True, text=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(group), str(wc), str(cpu)], env=e, capture_output=True, text=True,
+                               timeout=150)
+        except subprocess.TimeoutExpired:
+            print("%-36s TIMED OUT" % name)
+            continue
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if line:
             d = json.loads(line[-1])
