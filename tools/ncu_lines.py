@@ -47,6 +47,9 @@ def sass_line_map(kernel):
 
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
+    mangled = kernel
+    if ":" in kernel:
+        kernel, mangled = kernel.split(":", 1)
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel],
                          capture_output=True, text=True).stdout
@@ -55,7 +58,8 @@ def main():
     hdr = rows[hi]
     col = {n: hdr.index(n) for n in ("Address", "Instructions Executed", "Thread Instructions Executed", "# Samples",
                                      "L1 Tag Requests Global", "L1 Wavefronts Shared")}
-    amap = sass_line_map(kernel)
+    # template instances: "k_fast_tiles:k_fast_tilesILb1" = ncu kernel-name regex : fragment of the mangled name in the cubin
+    amap = sass_line_map(mangled)
     agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
     base = None
     for r in rows[hi + 1:]:
