@@ -871,8 +871,10 @@ __device__ __forceinline__ int qt_quadrant(short4 r, int x, int y) {
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);   // n1, n2, n3, n4 of :517-531
 }
 
-// Exclusive scan of v[0..n) in shared memory (in place); returns the total to every thread.
-__device__ int block_excl_scan(int* v, int n, int* scratch) {
+// Exclusive scan of v[0..n) (in place); returns the total to every thread.  Two block barriers: the warp totals go through one of
+// two scratch rows (`*flip` alternates them, so a call never overwrites the row the slowest warp of the previous call may still be
+// reading), and every warp scans the <= 32 warp totals itself with shuffles.
+__device__ int block_excl_scan(int* v, int n, int* scratch /* [2][32] */, int* flip) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ipt = (n + nt - 1) / nt;
     const int beg = min(tid * ipt, n), end = min(beg + ipt, n);
@@ -885,23 +887,19 @@ __device__ int block_excl_scan(int* v, int n, int* scratch) {
         const int t = __shfl_up_sync(ORBX_FULL_MASK, inc, o);
         if (lane >= o) inc += t;
     }
-    __syncthreads();  // scratch may still be read from a previous call
-    if (lane == 31) scratch[wid] = inc;
+    int* row = scratch + 32 * (*flip);
+    *flip ^= 1;
+    if (lane == 31) row[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-        const int w = lane < nw ? scratch[lane] : 0;
-        int winc = w;
+    const int w = lane < nw ? row[lane] : 0;
+    int winc = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(ORBX_FULL_MASK, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < nw) scratch[lane] = winc - w;
-        if (lane == 31) scratch[32] = winc;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(ORBX_FULL_MASK, winc, o);
+        if (lane >= o) winc += t;
     }
-    __syncthreads();
-    int run = scratch[wid] + inc - sum;
-    const int total = scratch[32];
+    const int total = __shfl_sync(ORBX_FULL_MASK, winc, 31);
+    int run = __shfl_sync(ORBX_FULL_MASK, winc - w, wid) + inc - sum;
     for (int i = beg; i < end; ++i) {
         const int x = v[i];
         v[i] = run;
@@ -951,8 +949,9 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level_base) {
     extern __shared__ __align__(16) uint8_t smem_qt[];
-    __shared__ int s_scratch[33];
+    __shared__ int s_scratch[64];
     __shared__ int s_nexp, s_cut, s_state;
+    int flip = 0;
 
     // grid (frames, levels): CTAs are handed out level-major, the biggest trees (level 0) first -- the longest jobs start first
     const int level = level_base + blockIdx.y, frame = blockIdx.x;
@@ -1006,7 +1005,7 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
     __syncthreads();
     for (int i = tid; i < L.nIni; i += nt) surv[i] = cntA[i] > 0;
     __syncthreads();
-    int nlive = block_excl_scan(surv, L.nIni, s_scratch);
+    int nlive = block_excl_scan(surv, L.nIni, s_scratch, &flip);
     for (int i = tid; i < L.nIni; i += nt)
         if (cntA[i] > 0) {
             rectB[surv[i]] = rectA[i];
@@ -1036,13 +1035,34 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
         for (int i = tid; i < nlive; i += nt) tmp[i] = cnt[i] > 1;
         if (tid == 0) { s_nexp = 0; s_cut = -1; }
         __syncthreads();
-        const int ns = block_excl_scan(tmp, nlive, s_scratch);
+        const int ns = block_excl_scan(tmp, nlive, s_scratch, &flip);
         if (ns == 0) break;  // every node is a single key: list size unchanged -> finish (:674)
-        for (int i = tid; i < nlive; i += nt)
+        for (int i = tid; i < nlive; i += nt) {
             if (cnt[i] > 1) seq[tmp[i]] = i;
+            surv[i] = i - tmp[i];        // position among the nodes that stay, valid whenever every node with > 1 key splits (no cut)
+            cbase[i] = -1;
+        }
         __syncthreads();
-        if (careful) {
-            // (size desc, later-created first) == (size desc, list position asc): bitonic sort of 64-bit keys, zero-padded
+        if (careful && NT >= 512 && ns <= 512) {
+            // (size desc, later-created first) == (size desc, list position asc).  Latency instances (512 / 1024 threads, one or a few
+            // frames) with a few hundred nodes: a rank sort -- every thread owns at most one element and walks the keys once, two
+            // barriers -- instead of the ~40 barriers of a bitonic network (with 256-thread CTAs in big groups the network is faster)
+            for (int s_ = tid; s_ < ns; s_ += nt) {
+                const int pos = seq[s_];
+                skey[s_] = ((unsigned long long)(unsigned)cnt[pos] << 32) | (unsigned)(0x7fffffff - pos);
+            }
+            __syncthreads();
+            for (int s_ = tid; s_ < ns; s_ += nt) {
+                const unsigned long long key = skey[s_];
+                int rank = 0;
+                for (int t = 0; t < ns; ++t) rank += skey[t] > key;
+                tmp[rank] = 0x7fffffff - (int)(unsigned)(key & 0xffffffffu);
+            }
+            __syncthreads();
+            for (int s_ = tid; s_ < ns; s_ += nt) seq[s_] = tmp[s_];
+            __syncthreads();
+        } else if (careful) {
+            // bitonic sort of the 64-bit keys, zero-padded to a power of two
             int n2 = 1;
             while (n2 < ns) n2 <<= 1;
             for (int s_ = tid; s_ < n2; s_ += nt) {
@@ -1075,7 +1095,7 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
         }
         if (tid == 0) tmp[ns] = 0;
         __syncthreads();
-        block_excl_scan(tmp, ns + 1, s_scratch);  // tmp[s] = children created before split s
+        block_excl_scan(tmp, ns + 1, s_scratch, &flip);  // tmp[s] = children created before split s
         // ---- how many splits are applied (careful phase stops once the list reaches N, :735) ----
         int nsplit = ns;
         if (careful) {
@@ -1088,15 +1108,24 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
             if (s_cut > 0) nsplit = s_cut;
         }
         const int T = tmp[nsplit];  // children created this pass
-        for (int i = tid; i < nlive; i += nt) { cbase[i] = -1; surv[i] = 1; }
-        __syncthreads();
-        for (int s_ = tid; s_ < nsplit; s_ += nt) {
-            const int pos = seq[s_];
-            cbase[pos] = tmp[s_];
-            surv[pos] = 0;
+        int nsurv;
+        if (nsplit == ns) {
+            // every node with more than one key splits: the survivors' positions were derived from the first scan
+            for (int s_ = tid; s_ < ns; s_ += nt) cbase[seq[s_]] = tmp[s_];
+            nsurv = nlive - ns;
+            __syncthreads();
+        } else {
+            // the careful phase stopped early: nodes behind the cut stay as they are
+            for (int i = tid; i < nlive; i += nt) surv[i] = 1;
+            __syncthreads();
+            for (int s_ = tid; s_ < nsplit; s_ += nt) {
+                const int pos = seq[s_];
+                cbase[pos] = tmp[s_];
+                surv[pos] = 0;
+            }
+            __syncthreads();
+            nsurv = block_excl_scan(surv, nlive, s_scratch, &flip);
         }
-        __syncthreads();
-        const int nsurv = block_excl_scan(surv, nlive, s_scratch);
         // children: list position T-1-(creation index); DivideNode geometry :488-514
         for (int s_ = tid; s_ < nsplit; s_ += nt) {
             const int pos = seq[s_];
@@ -1207,7 +1236,7 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
         rec[i] = o;
     }
     __syncthreads();
-    const int nlap = block_excl_scan(tmp, nout, s_scratch);
+    const int nlap = block_excl_scan(tmp, nout, s_scratch, &flip);
     for (int i = tid; i < nout; i += nt) rec[i].lap_before = tmp[i];
     if (tid == 0) ws.level_count[frame * plan.nlevels + level] = make_int2(nout, nlap);
 }
