@@ -470,3 +470,22 @@ def test_batch_path_never_reads_the_border(gpu, oracle, monkeypatch, w, h):
                 assert np.array_equal(ext.blurred_level(l, frame=f), ob), (f, l)
             assert np.array_equal(ext.pyramid_level(l, frame=f, with_border=True), o.level_plane(l)), (f, l)
     ext.close()
+
+
+def test_distribute_octtree_rejects_keys_outside_the_box(gpu):
+    """Keys are box coordinates, 0 <= x < maxX - minX.  A key outside would index past vpIniNodes in the reference (undefined
+    behaviour, ORBextractor.cc:574) and past the node table on the device: rejected up front with ORBX_ERR_BAD_ARGUMENT."""
+    ext = gpu.ORBextractor(1000, 1.2, 8, 20, 7)
+    keys = np.zeros(3, gpu.KP_DTYPE)
+    keys["x"], keys["y"], keys["response"] = [10, 50, 90], [10, 20, 30], [30, 40, 50]
+    ok = ext.DistributeOctTree(keys, 16, 16 + 100, 16, 16 + 80, 10)
+    assert len(ok) == 3
+    for bad_x, bad_y in ((100, 10), (4000, 10), (10, 81), (-1, 10), (10.5, 10)):
+        k2 = keys.copy()
+        k2["x"][1], k2["y"][1] = bad_x, bad_y
+        with pytest.raises(gpu.OrbxError) as ei:
+            ext.DistributeOctTree(k2, 16, 16 + 100, 16, 16 + 80, 10)
+        assert ei.value.code == -2
+    # the handle keeps working after the rejected calls
+    assert len(ext.DistributeOctTree(keys, 16, 16 + 100, 16, 16 + 80, 10)) == 3
+    ext.close()
