@@ -1040,7 +1040,8 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
                 pf[(size_t)((t & 7) * 32 + (t >> 3)) * 4 + slot] = (float)kPatternHost[4 * t + c];
             }
         // IC_Angle weight words: byte k of the aligned row window is patch column u = k - al - 15 (:82-97)
-        std::vector<int2> aw((size_t)4 * 31 * ORBX_ANGLE_WORDS);
+        // {u bytes, v bytes}, both signed and zero outside the circle; rows 31, 32 stay zero (k_describe steps three rows at a time)
+        std::vector<int2> aw((size_t)4 * ORBX_ANGLE_ROWS * ORBX_ANGLE_WORDS, make_int2(0, 0));
         for (int al = 0; al < 4; ++al)
             for (int row = 0; row < 31; ++row)
                 for (int wd = 0; wd < ORBX_ANGLE_WORDS; ++wd) {
@@ -1051,10 +1052,10 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
                         const int au = uu < 0 ? -uu : uu;
                         if (au <= ORBX_HALF_PATCH && au <= h->umax[v < 0 ? -v : v]) {
                             wu |= (unsigned)(uu & 0xff) << (8 * bb);
-                            wm |= 1u << (8 * bb);
+                            wm |= (unsigned)(v & 0xff) << (8 * bb);
                         }
                     }
-                    aw[((size_t)al * 31 + row) * ORBX_ANGLE_WORDS + wd] = make_int2((int)wu, (int)wm);
+                    aw[((size_t)al * ORBX_ANGLE_ROWS + row) * ORBX_ANGLE_WORDS + wd] = make_int2((int)wu, (int)wm);
                 }
         if (e == cudaSuccess) e = cudaMalloc(&h->d_pattern_f, pf.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(h->d_pattern_f, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice);

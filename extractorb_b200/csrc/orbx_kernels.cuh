@@ -1433,6 +1433,7 @@ __device__ __forceinline__ float2 orbx_add2(float2 a, float2 b) {
 
 #define ORBX_DESC_WARPS 8
 #define ORBX_ANGLE_WORDS 9   // 31 patch columns + up to 3 bytes of alignment slack = 9 aligned words per row
+#define ORBX_ANGLE_ROWS 33   // 31 patch rows + 2 all-zero rows: eleven steps of three rows
 
 // glibc's sinf / cosf (sysdeps/ieee754/flt-32/s_sincosf.h, the ARM optimized-routines algorithm) for 0 <= y < 120:
 // quadrant n = round(y * 2/pi) through a scaled float->int conversion, x = y - n * pi/2 in double, then a degree-7 sine or
@@ -1561,25 +1562,26 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
         __pipeline_commit();
     }
 
-    // ---- IC_Angle on the un-blurred level: 31 rows x 9 aligned words, IDP.4A against per-alignment
-    // weight words (u inside the circle, else 0) and mask words (1 inside the circle) ----
+    // ---- IC_Angle on the un-blurred level: 31 rows x 9 aligned words, IDP.4A against per-alignment weight words: u inside the
+    // circle (else 0) for m10, v = row - 15 inside the circle (else 0) for m01.  Lanes 0..26 hold three rows of nine words and step
+    // three rows at a time: every address is the lane's first one plus a constant.  The table has 33 rows (31, 32: all zero), so
+    // the last step needs no row test; the pixels it multiplies by zero are plane rows cy+16, cy+17 (inside the bordered plane).
     const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
     const int col0 = ORBX_PADL + cx - ORBX_HALF_PATCH;
     const int al = col0 & 3;
-    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(plane + (long long)(ORBX_EDGE + cy - ORBX_HALF_PATCH) * L.pitch + (col0 - al));
-    const int2* wt = ws.angle_w + al * (31 * ORBX_ANGLE_WORDS);
-    const int pw = L.pitch >> 2;
     int m10 = 0, m01 = 0;
+    if (lane < 3 * ORBX_ANGLE_WORDS) {
+        const int r0 = (lane * 57) >> 9;                       // lane / 9
+        const uint8_t* p8 = plane + (long long)(ORBX_EDGE + cy - ORBX_HALF_PATCH + r0) * L.pitch + (col0 - al) + 4 * (lane - ORBX_ANGLE_WORDS * r0);
+        const long long step = 3LL * L.pitch;
+        const int2* wt = ws.angle_w + al * (ORBX_ANGLE_ROWS * ORBX_ANGLE_WORDS) + lane;
 #pragma unroll
-    for (int it = 0; it < (31 * ORBX_ANGLE_WORDS + 31) / 32; ++it) {
-        const int i = it * 32 + lane;
-        if (i < 31 * ORBX_ANGLE_WORDS) {
-            const int row = (i * 57) >> 9;                 // i / 9 for i < 288
-            const int wd = i - row * ORBX_ANGLE_WORDS;
-            const unsigned px = __ldg(p32 + row * pw + wd);
-            const int2 w = __ldg(wt + i);
+        for (int it = 0; it < ORBX_ANGLE_ROWS / 3; ++it) {
+            const unsigned px = __ldg(reinterpret_cast<const uint32_t*>(p8));
+            p8 += step;
+            const int2 w = __ldg(wt + it * 3 * ORBX_ANGLE_WORDS);
             m10 = dp4a_u8_s8(px, w.x, m10);
-            m01 += (row - ORBX_HALF_PATCH) * (int)__dp4a(px, (unsigned)w.y, 0u);
+            m01 = dp4a_u8_s8(px, w.y, m01);
         }
     }
 #pragma unroll

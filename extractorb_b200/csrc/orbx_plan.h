@@ -136,7 +136,7 @@ struct OrbxWs {
     const uint8_t* tmaps_rs;   // ... entry l over the plane of level l-1, box = staging pitch x rows of k_pyr_resize<.., true>, or NULL
     const uint8_t* slot_level; // level of every kept-keypoint slot of a frame (kp_total bytes)
     const float* pattern_f;   // rBRIEF tests as floats, layout [bit k][descriptor byte][x0, x1, y0, y1]
-    const int2* angle_w;      // IC_Angle weights [4 alignments][31 rows][9 words] = {u bytes, mask bytes}
+    const int2* angle_w;      // IC_Angle weights [4 alignments][33 rows][9 words] = {u bytes, v bytes} (signed, 0 outside the circle)
     const uint32_t* blur_tiles; // blur tile table: level | tile_x << 8 | tile_y << 20
 };
 
