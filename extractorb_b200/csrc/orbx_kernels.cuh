@@ -1431,6 +1431,13 @@ __device__ __forceinline__ float2 orbx_add2(float2 a, float2 b) {
     return *reinterpret_cast<float2*>(&d);
 }
 
+// Shared-memory byte load from a 32-bit shared address.  Not volatile: the scheduler may move it, its address operand orders it.
+__device__ __forceinline__ unsigned orbx_lds_u8(unsigned saddr) {
+    unsigned v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 #define ORBX_DESC_WARPS 8
 #define ORBX_ANGLE_WORDS 9   // 31 patch columns + up to 3 bytes of alignment slack = 9 aligned words per row
 #define ORBX_ANGLE_ROWS 33   // 31 patch rows + 2 all-zero rows: eleven steps of three rows
@@ -1514,22 +1521,16 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     const int2* lc = ws.level_count + frame * plan.nlevels;
     int2 mine = make_int2(0, 0);
     if (lane < plan.nlevels) mine = lc[lane];
-    int incn = mine.x, incl = mine.y;
-#pragma unroll
-    for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) {
-        const int tn = __shfl_up_sync(ORBX_FULL_MASK, incn, o), tl = __shfl_up_sync(ORBX_FULL_MASK, incl, o);
-        if (lane >= o) { incn += tn; incl += tl; }
-    }
-    const int n_total = __shfl_sync(ORBX_FULL_MASK, incn, ORBX_MAX_LEVELS - 1);
-    const int lap_total = __shfl_sync(ORBX_FULL_MASK, incl, ORBX_MAX_LEVELS - 1);
+    // warp-wide integer sums are one instruction each (REDUX): totals, and the sums over the levels below this one
+    const int n_total = __reduce_add_sync(ORBX_FULL_MASK, mine.x), lap_total = __reduce_add_sync(ORBX_FULL_MASK, mine.y);
     const long long fo = (long long)(frame_out0 + frame);
     if (slot == 0 && lane == 0 && counts) {
         counts[2 * fo] = n_total;
         counts[2 * fo + 1] = n_total - lap_total;  // monoIndex, the reference's return value (:1161)
     }
     const int n_level = __shfl_sync(ORBX_FULL_MASK, mine.x, level);
-    const int n_before = __shfl_sync(ORBX_FULL_MASK, incn - mine.x, level);
-    const int lap_before = __shfl_sync(ORBX_FULL_MASK, incl - mine.y, level);
+    const int n_before = __reduce_add_sync(ORBX_FULL_MASK, lane < level ? mine.x : 0);
+    const int lap_before = __reduce_add_sync(ORBX_FULL_MASK, lane < level ? mine.y : 0);
     if (idx >= n_level) return;
     const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
@@ -1608,22 +1609,28 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
         __pipeline_wait_prior(0);
     }
     __syncwarp();
-    // sample index = (round(r)+18)*pitch + round(c)+18+o0; the rounding bias of both terms is folded into K
-    const int K = (int)((unsigned)(18 - ORBX_RND_BIAS) * (unsigned)ORBX_DESC_PP + (unsigned)(18 + o0 - ORBX_RND_BIAS));   // wraps, like the index arithmetic
+    // Sample address = patch + (round(r)+18)*64 + round(c)+18+o0.  The constant parts ride in the rounding constants: adding
+    // 1.5*2^23 + k (k an EVEN integer: ties still go to the even neighbour, like cvRound) leaves BIAS + k + round(v) in the low bits,
+    // so the row term carries the +18, the column term the patch's shared address + 18 + o0 less its odd bit, and one register
+    // holds the rest (the two biases, mod 2^32, and that odd bit): address = (rbits << 6) + cbits + kreg, two integer instructions.
+    const unsigned patch_sa = (unsigned)__cvta_generic_to_shared(patch) + 18u + (unsigned)o0;
+    const float mr = ORBX_RND_MAGIC + 18.0f, mc = (float)(12582912u + (patch_sa & ~1u));      // exact: integers below 2^24
+    unsigned kreg = (patch_sa & 1u) - 65u * (unsigned)ORBX_RND_BIAS;
+    asm volatile("" : "+r"(kreg) :: "memory");              // the loads below (plain asm, free to be scheduled) stay behind the wait above
     const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
     // Both points of a test share Blackwell's packed FP32 instructions: FMUL2 for the four products, scalar adds (see orbx_mul2),
     // FADD2 for the rounding constant -- the same bits as sixteen scalar operations in ten.  x*a - y*b is x*a + y*(-b): negation is exact.
-    const float2 aa = make_float2(a, a), bb = make_float2(b, b), nb = make_float2(-b, -b), mm = make_float2(ORBX_RND_MAGIC, ORBX_RND_MAGIC);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b), nb = make_float2(-b, -b), mmr = make_float2(mr, mr), mmc = make_float2(mc, mc);
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float4 t = __ldg(pat + k * 32);   // test 8*lane + k: x0, x1, y0, y1
         const float2 px = make_float2(t.x, t.y), py = make_float2(t.z, t.w);
         const float2 xb = orbx_mul2(px, bb), ya = orbx_mul2(py, aa), xa = orbx_mul2(px, aa), yb = orbx_mul2(py, nb);
-        const float2 r = orbx_add2(make_float2(__fadd_rn(xb.x, ya.x), __fadd_rn(xb.y, ya.y)), mm);
-        const float2 c = orbx_add2(make_float2(__fadd_rn(xa.x, yb.x), __fadd_rn(xa.y, yb.y)), mm);
-        const int t0 = patch[__float_as_int(r.x) * ORBX_DESC_PP + __float_as_int(c.x) + K];
-        const int t1 = patch[__float_as_int(r.y) * ORBX_DESC_PP + __float_as_int(c.y) + K];
+        const float2 r = orbx_add2(make_float2(__fadd_rn(xb.x, ya.x), __fadd_rn(xb.y, ya.y)), mmr);
+        const float2 c = orbx_add2(make_float2(__fadd_rn(xa.x, yb.x), __fadd_rn(xa.y, yb.y)), mmc);
+        const unsigned t0 = orbx_lds_u8(((unsigned)__float_as_int(r.x) << 6) + (unsigned)__float_as_int(c.x) + kreg);
+        const unsigned t1 = orbx_lds_u8(((unsigned)__float_as_int(r.y) << 6) + (unsigned)__float_as_int(c.y) + kreg);
         val |= (t0 < t1) << k;
     }
 
@@ -1635,19 +1642,17 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     const int out_idx = lapping ? (n_total - 1 - laps_before) : (n_before + idx - laps_before);
     if (lane == 0) recp->angle = angle;
     if (out_idx < cap_per_frame) {
-        if (desc_out) desc_out[(fo * cap_per_frame + out_idx) * 32 + lane] = (uint8_t)val;
+        const long long orow = fo * cap_per_frame + out_idx;
+        if (desc_out) desc_out[orow * 32 + lane] = (uint8_t)val;
         if (kps_out && lane < 7) {
-            float f;
-            switch (lane) {
-                case 0: f = xs; break;
-                case 1: f = ys; break;
-                case 2: f = L.kp_size; break;
-                case 3: f = angle; break;
-                case 4: f = rec.response; break;
-                case 5: f = __int_as_float(level); break;
-                default: f = __int_as_float(-1); break;
-            }
-            reinterpret_cast<float*>(kps_out)[(fo * cap_per_frame + out_idx) * 7 + lane] = f;
+            float f = xs;                                      // cv::KeyPoint: pt.x, pt.y, size, angle, response, octave, class_id
+            f = lane == 1 ? ys : f;
+            f = lane == 2 ? L.kp_size : f;
+            f = lane == 3 ? angle : f;
+            f = lane == 4 ? rec.response : f;
+            f = lane == 5 ? __int_as_float(level) : f;
+            f = lane == 6 ? __int_as_float(-1) : f;
+            reinterpret_cast<float*>(kps_out)[orow * 7 + lane] = f;
         }
     }
 }
