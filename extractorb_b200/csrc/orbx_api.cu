@@ -56,6 +56,7 @@ struct PlanEntry {
     int blur_tiles = 0;
     int rs_rows[ORBX_MAX_LEVELS] = {0};     // resize kernel: staged source rows / row pitch (bytes) per level
     int rs_pitch[ORBX_MAX_LEVELS] = {0};
+    int rs_pairs[ORBX_MAX_LEVELS] = {0};    // 1: source columns advance by <= 2 per destination column (two-column horizontal pass)
     int rs_launch_pitch[ORBX_MAX_LEVELS] = {0};  // staging pitch actually used at launch (ORBX_RS_PITCH for the specialised instance)
     // CUDA graph of the whole launch sequence for small launch groups (latency path), keyed by its arguments
     struct GraphKey {
@@ -288,6 +289,11 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
                 cols = std::max(cols, std::min(pe->xtab[V.xtab_off + xl].x + 1, S.w - 1) - pe->xtab[V.xtab_off + x0].x + 1);
             }
             pe->rs_rows[l] = rows;
+            pe->rs_pairs[l] = 1;
+            for (int x = 0; x + 1 < V.w; ++x) {
+                const int dxs = pe->xtab[V.xtab_off + x + 1].x - pe->xtab[V.xtab_off + x].x;
+                if (dxs < 0 || dxs > 2) pe->rs_pairs[l] = 0;
+            }
             {
                 const bool area_l = pe->xtab[V.xtab_off].y == -1;
                 const int pp = (int)align_up(cols + 15 + 15, 16);
@@ -718,16 +724,16 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             const int pitch = fixed ? ORBX_RS_PITCH : pe->rs_pitch[l];
             const size_t smem = rs_smem_bytes(pe->rs_rows[l], pitch);
             if (lat) {
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else k_pyr_resize<false, 0, ORBX_RS_TH_LAT><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
             } else {
                 const bool tma = ws.tmaps_rs != nullptr && !area;
-                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (fixed && tma) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else if (tma) k_pyr_resize<false, 0, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
-                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch);
+                if (area) k_pyr_resize<true, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else if (fixed && tma) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else if (fixed) k_pyr_resize<false, ORBX_RS_PITCH, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else if (tma) k_pyr_resize<false, 0, ORBX_RS_TH, true><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
+                else k_pyr_resize<false, 0, ORBX_RS_TH><<<grd, 256, smem, st>>>(P, ws, l, pe->rs_rows[l], pitch, pe->rs_pairs[l]);
             }
             ++launches;
             if (per_level) { const int rb = level_branch(l); if (rb != ORBX_OK) return rb; }

@@ -106,6 +106,37 @@ __device__ __forceinline__ void rs_hpass(const uint8_t* __restrict__ q0, const u
     }
 }
 
+// Horizontal pass, two adjacent destination columns per thread (levels whose source columns advance by at most 2 per destination
+// column, i.e. every scale factor <= 2): the <= 7 source bytes both columns need lie in two aligned words; one PRMT (selector fixed
+// per thread) lines up {u0, u1} of column A in the low half and of column B in the high half, and each H = u0*a0 + u1*a1 is ONE
+// IDP.2A against the column's {a0, a1} 16-bit pair (the x table's own format).  Nine instructions per pair and row instead of twelve.
+template <int NG, int PITCH>
+__device__ __forceinline__ void rs_hpass2(const uint32_t* __restrict__ q, uint32_t* __restrict__ hq, unsigned sel, unsigned ca, unsigned cb,
+                                          int g, int ng_rt, int nrows, int pitch_rt) {
+    const int ng = NG ? NG : ng_rt;
+    const int step = ng * ((PITCH ? PITCH : pitch_rt) >> 2);         // words
+    auto h2 = [&](uint32_t w0, uint32_t w1) -> uint32_t {
+        const uint32_t v = __byte_perm(w0, w1, sel);
+        const uint32_t ha = __dp2a_lo(ca, v, 0u), hb = __dp2a_hi(cb, v, 0u);
+        return (ha >> 4) | ((hb << 12) & 0xffff0000u);
+    };
+    int r = g;
+#pragma unroll 1
+    for (; r + 3 * ng < nrows; r += 4 * ng) {                     // four rows per iteration: loads first, then the math
+        const uint32_t a0 = q[0], a1 = q[1], b0 = q[step], b1 = q[step + 1];
+        const uint32_t c0 = q[2 * step], c1 = q[2 * step + 1], d0 = q[3 * step], d1 = q[3 * step + 1];
+        hq[0] = h2(a0, a1);
+        hq[ng * (ORBX_RS_TW / 2)] = h2(b0, b1);
+        hq[2 * ng * (ORBX_RS_TW / 2)] = h2(c0, c1);
+        hq[3 * ng * (ORBX_RS_TW / 2)] = h2(d0, d1);
+        q += 4 * step; hq += 4 * ng * (ORBX_RS_TW / 2);
+    }
+    for (; r < nrows; r += ng) {
+        hq[0] = h2(q[0], q[1]);
+        q += step; hq += ng * (ORBX_RS_TW / 2);
+    }
+}
+
 #define ORBX_RS_PITCH 192     // staging pitch of the specialised instance (covers scale factors up to ~1.25)
 
 // TH: tile height.  ORBX_RS_TH for throughput; ORBX_RS_TH_LAT for one or two frames, where a level is a handful of tiles and
@@ -137,7 +168,7 @@ __device__ __forceinline__ void border_right_word(const uint32_t* __restrict__ s
 // one bulk tensor copy instead of ~1000 16-byte cp.async.
 template <bool AREA, int PITCH, int TH, bool TMA = false>
 __global__ void __launch_bounds__(256)
-k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt) {
+k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, int src_rows_max, int src_pitch_rt, int pairs) {
     extern __shared__ __align__(128) uint8_t smem_rs[];
     __shared__ __align__(8) unsigned long long s_bar;
     const int src_pitch_s = PITCH ? PITCH : src_pitch_rt;
@@ -202,7 +233,25 @@ k_pyr_resize(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int level, 
     // groups of 128 columns; partial tiles: 256 / tw row groups of tw columns, so that no lane idles ----
     {
         uint16_t* s_h = reinterpret_cast<uint16_t*>(s_hb);
-        if (tw == ORBX_RS_TW) {
+        if (!AREA && pairs) {
+            // column pairs: 64 pairs x 4 row groups on a full tile, 256 / pairs row groups on a partial one
+            const int np = (tw + 1) >> 1;
+            const bool full = tw == ORBX_RS_TW;
+            const int ng = full ? 4 : 256 / np;
+            const int g = full ? tid >> 6 : tid / np, c2 = full ? tid & 63 : tid - g * np;
+            if (g < ng) {
+                const int ca = 2 * c2, cb = min(ca + 1, tw - 1);
+                const int2 xa = __ldg(&xtab[x0 + ca]), xb = __ldg(&xtab[x0 + cb]);
+                const int off = xa.x - sx_lo + al;                 // staged byte of column A's first tap
+                const unsigned pa0 = off & 3, pa1 = pa0 + (min(xa.x + 1, S.w - 1) - xa.x);
+                const unsigned pb0 = pa0 + (xb.x - xa.x), pb1 = pb0 + (min(xb.x + 1, S.w - 1) - xb.x);      // <= 6
+                const unsigned sel = pa0 | (pa1 << 4) | (pb0 << 8) | (pb1 << 12);
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_src + g * src_pitch_s) + (off >> 2);
+                uint32_t* hq = reinterpret_cast<uint32_t*>(s_h) + g * (ORBX_RS_TW / 2) + c2;
+                if (full) rs_hpass2<4, PITCH>(q, hq, sel, (unsigned)xa.y, (unsigned)xb.y, g, 4, nrows, src_pitch_s);
+                else rs_hpass2<0, PITCH>(q, hq, sel, (unsigned)xa.y, (unsigned)xb.y, g, ng, nrows, src_pitch_s);
+            }
+        } else if (tw == ORBX_RS_TW) {
             const int c = tid & (ORBX_RS_TW - 1), g = tid >> 7;
             const int2 xt = __ldg(&xtab[x0 + c]);
             const uint8_t* q0 = s_src + (xt.x - sx_lo + al) + g * src_pitch_s;
