@@ -909,10 +909,12 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
 // Keys never move: each key carries the list position of its node and the split geometry is
 // recomputed from the node rectangle.
 // =================================================================================================
-#define ORBX_QT_THREADS 256      // large launch groups (throughput)
+#define ORBX_QT_THREADS 128      // large launch groups (throughput) whose largest remaining level is below ORBX_QT_MID_PIXELS
+#define ORBX_QT_THREADS_MID 256  // large launch groups otherwise (the mid levels of a 4K pyramid hold thousands of candidates each)
 #define ORBX_QT_THREADS_LAT 512  // small launch groups: one CTA per level is latency bound
 #define ORBX_QT_THREADS_BIG 1024 // levels of >= ORBX_QT_BIG_PIXELS pixels (tens of thousands of candidates per quadtree)
 #define ORBX_QT_BIG_PIXELS 1000000
+#define ORBX_QT_MID_PIXELS 600000
 
 __device__ __forceinline__ int qt_quadrant(short4 r, int x, int y) {
     const int mx = r.x + ((r.y - r.x + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2), :488
