@@ -113,9 +113,11 @@ def test_synthetic_vs_oracle(gpu, oracle, w, h, nf, nl, lap):
     check_against_oracle(gpu, oracle, img, nf=nf, nl=nl, lap=lap)
 
 
-@pytest.mark.parametrize("scale,nl,ini,mn", [(1.5, 5, 25, 10), (2.0, 3, 20, 7), (1.1, 10, 15, 5), (1.2, 8, 7, 20)])
+@pytest.mark.parametrize("scale,nl,ini,mn", [(1.5, 5, 25, 10), (2.0, 3, 20, 7), (1.1, 10, 15, 5), (1.2, 8, 7, 20),
+                                             (1.9, 3, 20, 7), (2.5, 3, 20, 7), (3.0, 2, 20, 7)])
 def test_other_scales_and_thresholds(gpu, oracle, scale, nl, ini, mn):
-    """scale 2.0 exercises OpenCV's exact-2x INTER_AREA path; (7, 20) has minThFAST > iniThFAST."""
+    """scale 2.0 exercises OpenCV's exact-2x INTER_AREA path; (7, 20) has minThFAST > iniThFAST; 1.9 the two-column horizontal
+    resize pass with source steps of 2; 2.5 and 3.0 its one-column fallback (source columns more than 2 apart)."""
     img = synth_frame(77, 640, 480)
     check_against_oracle(gpu, oracle, img, nf=1200, scale=scale, nl=nl, ini=ini, mn=mn)
 
