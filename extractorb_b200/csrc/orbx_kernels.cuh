@@ -1389,10 +1389,7 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
     // partial tiles (right / bottom edge of a level): horizontal sums nobody reads are not computed
     const int xq_end = min(ORBX_BLUR_TW / 4, (L.blur_pitch - x0 + 3) >> 2);          // 4-pixel groups with an output column
     const int rp_end = min(SROWS / 2, ((min(ORBX_BLUR_TH, L.h - y0) + 1) >> 1) + 3);   // row pairs feeding an output row
-    for (int i = tid; i < (SROWS / 2) * (ORBX_BLUR_TW / 4); i += 256) {
-        const int rp = i >> 5, xq = i & 31;
-        if (rp >= rp_end) break;
-        if (xq >= xq_end) continue;
+    auto hitem = [&](int rp, int xq) {
         uint32_t h[2][4];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -1406,37 +1403,61 @@ k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) 
             }
         }
         uint4 o;
-        o.x = h[0][0] | (h[1][0] << 16); o.y = h[0][1] | (h[1][1] << 16);
-        o.z = h[0][2] | (h[1][2] << 16); o.w = h[0][3] | (h[1][3] << 16);
+        o.x = __byte_perm(h[0][0], h[1][0], 0x5410); o.y = __byte_perm(h[0][1], h[1][1], 0x5410);      // sums < 2^16: rows 2k | 2k+1 << 16
+        o.z = __byte_perm(h[0][2], h[1][2], 0x5410); o.w = __byte_perm(h[0][3], h[1][3], 0x5410);
         *reinterpret_cast<uint4*>(s_h2 + rp * ORBX_BLUR_TW + 4 * xq) = o;
+    };
+    // tiles on a level's right edge hold xq_end < 32 groups per row: items are dealt out linearly there, so that no lane idles
+    // (a level of 257 columns has a tile column with ONE group per row)
+    const unsigned xq_magic = (1u << 20) / (unsigned)xq_end + 1u;      // i / xq_end for i < 2^11
+    if (xq_end == ORBX_BLUR_TW / 4) {
+        for (int i = tid; i < (SROWS / 2) * (ORBX_BLUR_TW / 4); i += 256) {
+            if ((i >> 5) >= rp_end) break;
+            hitem(i >> 5, i & 31);
+        }
+    } else {
+        for (int i = tid; i < rp_end * xq_end; i += 256) {
+            const int rp = (int)(((unsigned)i * xq_magic) >> 20);
+            hitem(rp, i - rp * xq_end);
+        }
     }
     __syncthreads();
     // ---- vertical: item = (two output rows 2q, 2q+1) x (4 pixels); both rows use row pairs q .. q+3 ----
     const unsigned WE01 = 18u | (34u << 8) | (48u << 16) | (56u << 24), WE23 = 48u | (34u << 8) | (18u << 16);
     const unsigned WO01 = (18u << 8) | (34u << 16) | (48u << 24), WO23 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
     uint8_t* out = ws.blur + (long long)frame * ws.blur_stride + L.blur_off;
-#pragma unroll
-    for (int it = 0; it < (ORBX_BLUR_TH / 2) * (ORBX_BLUR_TW / 4) / 256; ++it) {
-        const int i = tid + it * 256;
-        const int q = i >> 5, xq = i & 31;
+    auto vitem = [&](int q, int xq) {
         const int y = y0 + 2 * q, x = x0 + 4 * xq;
-        if (y >= L.h || x >= L.blur_pitch) continue;
         const uint4 p0 = *reinterpret_cast<const uint4*>(s_h2 + (q + 0) * ORBX_BLUR_TW + 4 * xq);
         const uint4 p1 = *reinterpret_cast<const uint4*>(s_h2 + (q + 1) * ORBX_BLUR_TW + 4 * xq);
         const uint4 p2 = *reinterpret_cast<const uint4*>(s_h2 + (q + 2) * ORBX_BLUR_TW + 4 * xq);
         const uint4 p3 = *reinterpret_cast<const uint4*>(s_h2 + (q + 3) * ORBX_BLUR_TW + 4 * xq);
         const uint32_t a0[4] = {p0.x, p0.y, p0.z, p0.w}, a1[4] = {p1.x, p1.y, p1.z, p1.w};
         const uint32_t a2[4] = {p2.x, p2.y, p2.z, p2.w}, a3[4] = {p3.x, p3.y, p3.z, p3.w};
-        uint32_t we = 0, wo = 0;
+        uint32_t ve[4], vo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t ve = __dp2a_hi(a3[j], WE23, __dp2a_lo(a2[j], WE23, __dp2a_hi(a1[j], WE01, __dp2a_lo(a0[j], WE01, 32768u))));
-            const uint32_t vo = __dp2a_hi(a3[j], WO23, __dp2a_lo(a2[j], WO23, __dp2a_hi(a1[j], WO01, __dp2a_lo(a0[j], WO01, 32768u))));
-            we |= (ve >> 16) << (8 * j);
-            wo |= (vo >> 16) << (8 * j);
+            ve[j] = __dp2a_hi(a3[j], WE23, __dp2a_lo(a2[j], WE23, __dp2a_hi(a1[j], WE01, __dp2a_lo(a0[j], WE01, 32768u))));
+            vo[j] = __dp2a_hi(a3[j], WO23, __dp2a_lo(a2[j], WO23, __dp2a_hi(a1[j], WO01, __dp2a_lo(a0[j], WO01, 32768u))));
         }
+        // V + 32768 < 2^24: the result byte is byte 2 of each sum; three PRMTs gather four of them
+        const uint32_t we = __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
+        const uint32_t wo = __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
         *reinterpret_cast<uint32_t*>(out + (long long)y * L.blur_pitch + x) = we;
         if (y + 1 < L.h) *reinterpret_cast<uint32_t*>(out + (long long)(y + 1) * L.blur_pitch + x) = wo;
+    };
+    const int nq = (min(ORBX_BLUR_TH, L.h - y0) + 1) >> 1;             // output row pairs of this tile
+    if (xq_end == ORBX_BLUR_TW / 4) {
+#pragma unroll
+        for (int it = 0; it < (ORBX_BLUR_TH / 2) * (ORBX_BLUR_TW / 4) / 256; ++it) {
+            const int i = tid + it * 256;
+            if ((i >> 5) < nq) vitem(i >> 5, i & 31);
+        }
+    } else {
+        for (int i = tid; i < nq * xq_end; i += 256) {
+            const int q = (int)(((unsigned)i * xq_magic) >> 20);
+            vitem(q, i - q * xq_end);
+        }
     }
 }
 
