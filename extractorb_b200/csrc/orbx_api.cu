@@ -770,10 +770,10 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         for (int l = 0; l < P.nlevels; ++l) ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_lvl_done[l], 0));
         ORBX_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         if (ws.tmaps_blur)
-            k_describe<true><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            k_describe<true><<<dim3((P.kp_total + 2 * ORBX_DESC_WARPS - 1) / (2 * ORBX_DESC_WARPS), nf), ORBX_DESC_WARPS * 32, 0, st>>>(
                 P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         else
-            k_describe<false><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            k_describe<false><<<dim3((P.kp_total + 2 * ORBX_DESC_WARPS - 1) / (2 * ORBX_DESC_WARPS), nf), ORBX_DESC_WARPS * 32, 0, st>>>(
                 P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         ++launches;
     } else if (stages & STAGES_KEYPOINTS) {
@@ -814,10 +814,10 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[4], st));
         nvtx_stage("orbx:describe");
         if (ws.tmaps_blur)
-            k_describe<true><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            k_describe<true><<<dim3((P.kp_total + 2 * ORBX_DESC_WARPS - 1) / (2 * ORBX_DESC_WARPS), nf), ORBX_DESC_WARPS * 32, 0, st>>>(
                 P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         else
-            k_describe<false><<<dim3((P.kp_total + ORBX_DESC_WARPS - 1) / ORBX_DESC_WARPS, nf), ORBX_DESC_WARPS * 32, 0, st>>>(
+            k_describe<false><<<dim3((P.kp_total + 2 * ORBX_DESC_WARPS - 1) / (2 * ORBX_DESC_WARPS), nf), ORBX_DESC_WARPS * 32, 0, st>>>(
                 P, ws, h->fc, d_kps, d_desc, cap_per_frame, d_counts, frame_out0);
         ++launches;
         if (se) ORBX_CUDA(cudaEventRecord(se->ev[5], st));
@@ -1043,11 +1043,12 @@ int orbx_create(const OrbxParams* prm, int device, OrbxHandle** out) {
     }
     {
         std::vector<float> pf(1024);
-        // device layout [k][lane][4]: test t = 8*lane + k (descriptor byte `lane`, bit k) so that a warp's loads coalesce
+        // device layout [k][hl][4]: test t = 16*hl + k (descriptor bytes 2 hl, 2 hl + 1 = bits 0..15 of lane hl's word) so that a
+        // half-warp's loads coalesce and the two half-warps of k_describe read the same words
         for (int t = 0; t < 256; ++t)
             for (int c = 0; c < 4; ++c) {
                 const int slot = c == 1 ? 2 : (c == 2 ? 1 : c);      // stored as (x0, x1, y0, y1): the two points side by side for the packed FP32 ops
-                pf[(size_t)((t & 7) * 32 + (t >> 3)) * 4 + slot] = (float)kPatternHost[4 * t + c];
+                pf[(size_t)((t & 15) * 16 + (t >> 4)) * 4 + slot] = (float)kPatternHost[4 * t + c];
             }
         // IC_Angle weight words: byte k of the aligned row window is patch column u = k - al - 15 (:82-97)
         // {u bytes, v bytes}, both signed and zero outside the circle; rows 31, 32 stay zero (k_describe steps three rows at a time)

@@ -1568,52 +1568,70 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned a, int b, int c) {
 #define ORBX_RND_BIAS 0x4B400000
 
 // TMA: the 37-row window of the blurred level arrives as one bulk tensor copy per keypoint (box 64 B x 37 rows from the level's
-// tensor map over the blur buffer, one mbarrier per warp) instead of 13 rounds of 4-byte cp.async with their index arithmetic.
+// tensor map over the blur buffer, one mbarrier per keypoint) instead of 13 rounds of 4-byte cp.async with their index arithmetic.
 // The box starts at a 16-byte aligned column (a box starting at an arbitrary byte never completed on the B200: trap), so it is
 // 64 bytes wide: up to 15 bytes of alignment slack + the 37 columns.
+//
+// A warp owns TWO keypoints (slots 2w, 2w+1): lanes 0..15 carry the first through everything that is per keypoint (level
+// bookkeeping, fastAtan2, sincos, the output records), lanes 16..31 the second, so those ~330 instructions are paid once per pair;
+// the moments of both run on 27 lanes each, one after the other, and meet in a reduction that costs what one did; every lane then
+// computes 16 tests = two descriptor bytes of its keypoint, and the two half-warps read the same pattern words (half the
+// pattern traffic per keypoint -- the kernel is bound by L1 / shared-memory wavefronts, not by issue slots).
 #define ORBX_DESC_PP 64        // patch row pitch in shared memory = TMA box width
+#define ORBX_DESC_PATCH (37 * ORBX_DESC_PP + 64)   // 2432 B: 128-byte aligned slots
 template <bool TMA>
-__global__ void __launch_bounds__(ORBX_DESC_WARPS * 32, 8)
+__global__ void __launch_bounds__(ORBX_DESC_WARPS * 32, 5)
 k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFloatConsts fc,
            void* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
            int cap_per_frame, int32_t* __restrict__ counts, int frame_out0) {
-    __shared__ __align__(128) uint8_t s_patch[ORBX_DESC_WARPS][37 * ORBX_DESC_PP + 64];     // 2432 B per warp: 128-byte aligned slots
-    __shared__ __align__(8) unsigned long long s_bar[ORBX_DESC_WARPS];
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * ORBX_DESC_WARPS + (threadIdx.x >> 5);
+    __shared__ __align__(128) uint8_t s_patch[ORBX_DESC_WARPS][2][ORBX_DESC_PATCH];
+    __shared__ __align__(8) unsigned long long s_bar[ORBX_DESC_WARPS][2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const int slot0 = 2 * (blockIdx.x * ORBX_DESC_WARPS + wib);
     const int frame = blockIdx.y;
-    if (slot >= plan.kp_total) return;
-    // level of this slot: one byte from the plan's slot table
-    const int level = __ldg(ws.slot_level + slot);
+    if (slot0 >= plan.kp_total) return;
+    // ---- this half's keypoint; a half without one (odd total, or a level that kept fewer keypoints than it has slots) shadows the
+    // other half -- same loads, no stores -- so that every warp-wide step below stays uniform ----
+    const int2* lc = ws.level_count + frame * plan.nlevels;
+    int2 mine = make_int2(0, 0);
+    if (lane < plan.nlevels) mine = lc[lane];
+    // per-frame sums of {keypoints, lapping keypoints} over all levels (REDUX); the frame's first warp reports them
+    const int n_total = __reduce_add_sync(ORBX_FULL_MASK, mine.x), lap_total = __reduce_add_sync(ORBX_FULL_MASK, mine.y);
+    const long long fo = (long long)(frame_out0 + frame);
+    if (slot0 == 0 && lane == 0 && counts) {
+        counts[2 * fo] = n_total;
+        counts[2 * fo + 1] = n_total - lap_total;  // monoIndex, the reference's return value (:1161)
+    }
+    int slot = slot0 + half;
+    int level = slot < plan.kp_total ? (int)__ldg(ws.slot_level + slot) : 0;
+    const int n_level = __shfl_sync(ORBX_FULL_MASK, mine.x, level);
+    const bool valid = slot < plan.kp_total && slot - plan.lv[level].kp_off < n_level;
+    {
+        const unsigned vb = __ballot_sync(ORBX_FULL_MASK, valid);
+        if (vb == 0u) return;
+        const int o_slot = __shfl_xor_sync(ORBX_FULL_MASK, slot, 16), o_level = __shfl_xor_sync(ORBX_FULL_MASK, level, 16);
+        if (!valid) { slot = o_slot; level = o_level; }
+    }
     const OrbxLevel& L = plan.lv[level];
     const int idx = slot - L.kp_off;
     OrbxKpRec* recp = ws.kprec + (long long)frame * ws.kp_stride + slot;
     const OrbxKpRec rec = *recp;
-    // ---- per-frame level prefix {keypoints, lapping keypoints} by warp scan ----
-    const int2* lc = ws.level_count + frame * plan.nlevels;
-    int2 mine = make_int2(0, 0);
-    if (lane < plan.nlevels) mine = lc[lane];
-    // warp-wide integer sums are one instruction each (REDUX): totals, and the sums over the levels below this one
-    const int n_total = __reduce_add_sync(ORBX_FULL_MASK, mine.x), lap_total = __reduce_add_sync(ORBX_FULL_MASK, mine.y);
-    const long long fo = (long long)(frame_out0 + frame);
-    if (slot == 0 && lane == 0 && counts) {
-        counts[2 * fo] = n_total;
-        counts[2 * fo + 1] = n_total - lap_total;  // monoIndex, the reference's return value (:1161)
-    }
-    const int n_level = __shfl_sync(ORBX_FULL_MASK, mine.x, level);
-    const int n_before = __reduce_add_sync(ORBX_FULL_MASK, lane < level ? mine.x : 0);
-    const int lap_before = __reduce_add_sync(ORBX_FULL_MASK, lane < level ? mine.y : 0);
-    if (idx >= n_level) return;
+    // the sums over the levels below each half's level
+    const int lvl_a = __shfl_sync(ORBX_FULL_MASK, level, 0), lvl_b = __shfl_sync(ORBX_FULL_MASK, level, 16);
+    const int nb_a = __reduce_add_sync(ORBX_FULL_MASK, lane < lvl_a ? mine.x : 0), nb_b = __reduce_add_sync(ORBX_FULL_MASK, lane < lvl_b ? mine.x : 0);
+    const int lb_a = __reduce_add_sync(ORBX_FULL_MASK, lane < lvl_a ? mine.y : 0), lb_b = __reduce_add_sync(ORBX_FULL_MASK, lane < lvl_b ? mine.y : 0);
+    const int n_before = half ? nb_b : nb_a, lap_before = half ? lb_b : lb_a;
     const int cx = (int)rec.x, cy = (int)rec.y;  // integral by construction
 
     // Stage the 37x37 window of the blurred level (|rotated offset| <= 18) into shared memory, issued first so that the copy
-    // overlaps the moment computation below: one TMA box, or aligned 32-bit cp.async copies.
+    // overlaps the moment computation below: one TMA box per keypoint, or aligned 32-bit cp.async copies.
     const int bp = L.blur_pitch;
     const int bx0 = cx - 18, o0 = TMA ? (bx0 & 15) : (bx0 & 3);
-    uint8_t* patch = s_patch[threadIdx.x >> 5];
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]);
+    uint8_t* patch = s_patch[wib][half];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[wib][half]);
     if (TMA) {
-        if (lane == 0) {
+        if (hl == 0) {
             orbx_mbar_init(bar, 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             orbx_mbar_expect_tx(bar, 37 * ORBX_DESC_PP);
@@ -1623,14 +1641,10 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
         const uint32_t* b32 = reinterpret_cast<const uint32_t*>(ws.blur + (long long)frame * ws.blur_stride + L.blur_off +
                                                                   (long long)(cy - 18) * bp + (bx0 - o0));
         const int bpw = bp >> 2;
-#pragma unroll
-        for (int it = 0; it < (37 * 11 + 31) / 32; ++it) {
-            const int i = it * 32 + lane;
-            if (i < 37 * 11) {
-                const int row = (i * 373) >> 12;               // i / 11 for i < 407
-                const int wd = i - row * 11;
-                __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(patch) + row * (ORBX_DESC_PP / 4) + wd, b32 + row * bpw + wd, 4);
-            }
+        for (int i = hl; i < 37 * 11; i += 16) {
+            const int row = (i * 373) >> 12;                   // i / 11 for i < 407
+            const int wd = i - row * 11;
+            __pipeline_memcpy_async(reinterpret_cast<uint32_t*>(patch) + row * (ORBX_DESC_PP / 4) + wd, b32 + row * bpw + wd, 4);
         }
         __pipeline_commit();
     }
@@ -1639,32 +1653,48 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     // circle (else 0) for m10, v = row - 15 inside the circle (else 0) for m01.  Lanes 0..26 hold three rows of nine words and step
     // three rows at a time: every address is the lane's first one plus a constant.  The table has 33 rows (31, 32: all zero), so
     // the last step needs no row test; the pixels it multiplies by zero are plane rows cy+16, cy+17 (inside the bordered plane).
-    const uint8_t* plane = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off;
-    const int col0 = ORBX_PADL + cx - ORBX_HALF_PATCH;
-    const int al = col0 & 3;
+    // Both keypoints of the warp go through the same 27 lanes: their patch corner, pitch and alignment come from lanes 0 / 16.
     int m10 = 0, m01 = 0;
-    if (lane < 3 * ORBX_ANGLE_WORDS) {
+    {
+        const int col0 = ORBX_PADL + cx - ORBX_HALF_PATCH;
+        const int al_h = col0 & 3;
+        const unsigned long long corner = (unsigned long long)(ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off +
+                                                               (long long)(ORBX_EDGE + cy - ORBX_HALF_PATCH) * L.pitch + (col0 - al_h));
         const int r0 = (lane * 57) >> 9;                       // lane / 9
-        const uint8_t* p8 = plane + (long long)(ORBX_EDGE + cy - ORBX_HALF_PATCH + r0) * L.pitch + (col0 - al) + 4 * (lane - ORBX_ANGLE_WORDS * r0);
-        const long long step = 3LL * L.pitch;
-        const int2* wt = ws.angle_w + al * (ORBX_ANGLE_ROWS * ORBX_ANGLE_WORDS) + lane;
+        const int wd4 = 4 * (lane - ORBX_ANGLE_WORDS * r0);
+        int sum10[2], sum01[2];
 #pragma unroll
-        for (int it = 0; it < ORBX_ANGLE_ROWS / 3; ++it) {
-            const unsigned px = __ldg(reinterpret_cast<const uint32_t*>(p8));
-            p8 += step;
-            const int2 w = __ldg(wt + it * 3 * ORBX_ANGLE_WORDS);
-            m10 = dp4a_u8_s8(px, w.x, m10);
-            m01 = dp4a_u8_s8(px, w.y, m01);
+        for (int k = 0; k < 2; ++k) {
+            const unsigned long long c_k = __shfl_sync(ORBX_FULL_MASK, corner, 16 * k);
+            const int pitch_k = __shfl_sync(ORBX_FULL_MASK, L.pitch, 16 * k), al_k = __shfl_sync(ORBX_FULL_MASK, al_h, 16 * k);
+            int a10 = 0, a01 = 0;
+            if (lane < 3 * ORBX_ANGLE_WORDS) {
+                const uint8_t* p8 = reinterpret_cast<const uint8_t*>(c_k) + (long long)r0 * pitch_k + wd4;
+                const long long step = 3LL * pitch_k;
+                const int2* wt = ws.angle_w + al_k * (ORBX_ANGLE_ROWS * ORBX_ANGLE_WORDS) + lane;
+#pragma unroll
+                for (int it = 0; it < ORBX_ANGLE_ROWS / 3; ++it) {
+                    const unsigned px = __ldg(reinterpret_cast<const uint32_t*>(p8));
+                    p8 += step;
+                    const int2 w = __ldg(wt + it * 3 * ORBX_ANGLE_WORDS);
+                    a10 = dp4a_u8_s8(px, w.x, a10);
+                    a01 = dp4a_u8_s8(px, w.y, a01);
+                }
+            }
+            sum10[k] = a10; sum01[k] = a01;
         }
-    }
+        // each half keeps the partial sums of ITS keypoint and receives the partner lane's: five shuffle steps reduce both keypoints
+        m10 = (half ? sum10[1] : sum10[0]) + __shfl_xor_sync(ORBX_FULL_MASK, half ? sum10[0] : sum10[1], 16);
+        m01 = (half ? sum01[1] : sum01[0]) + __shfl_xor_sync(ORBX_FULL_MASK, half ? sum01[0] : sum01[1], 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(ORBX_FULL_MASK, m10, o);
-        m01 += __shfl_xor_sync(ORBX_FULL_MASK, m01, o);
+        for (int o = 8; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(ORBX_FULL_MASK, m10, o);
+            m01 += __shfl_xor_sync(ORBX_FULL_MASK, m01, o);
+        }
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10, fc);
 
-    // ---- rBRIEF on the blurred level: lane i computes descriptor byte i ----
+    // ---- rBRIEF on the blurred level: lane hl of a half computes descriptor bytes 2 hl, 2 hl + 1 of its keypoint ----
     const float rad = __fmul_rn(angle, fc.deg2rad);
     // The reference calls glibc's cosf / sinf (:111).  orbx_glibc_sincosf restates that algorithm (a double-precision
     // polynomial after a quadrant reduction); it equals glibc 2.39 on every float in [0, 6.5] (checked exhaustively on the
@@ -1672,7 +1702,7 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     float a, b;
     orbx_glibc_sincosf(rad, &b, &a);
     if (TMA) {
-        __syncwarp();                                           // lane 0 has initialised the barrier and issued the copy
+        __syncwarp();                                           // lanes 0 / 16 have initialised the barriers and issued the copies
         unsigned spins = 0;
         while (!orbx_mbar_try_wait(bar, 0)) {
             if (++spins > (1u << 18)) __trap();                 // a copy that never lands must fail loudly, not hang the device
@@ -1689,42 +1719,47 @@ k_describe(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const OrbxFlo
     const float mr = ORBX_RND_MAGIC + 18.0f, mc = (float)(12582912u + (patch_sa & ~1u));      // exact: integers below 2^24
     unsigned kreg = (patch_sa & 1u) - 65u * (unsigned)ORBX_RND_BIAS;
     asm volatile("" : "+r"(kreg) :: "memory");              // the loads below (plain asm, free to be scheduled) stay behind the wait above
-    const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + lane;   // layout [k][lane]: coalesced
+    const float4* pat = reinterpret_cast<const float4*>(ws.pattern_f) + hl;   // layout [k][hl]: both halves read the same 256 bytes
     // Both points of a test share Blackwell's packed FP32 instructions: FMUL2 for the four products, scalar adds (see orbx_mul2),
     // FADD2 for the rounding constant -- the same bits as sixteen scalar operations in ten.  x*a - y*b is x*a + y*(-b): negation is exact.
     const float2 aa = make_float2(a, a), bb = make_float2(b, b), nb = make_float2(-b, -b), mmr = make_float2(mr, mr), mmc = make_float2(mc, mc);
-    int val = 0;
+    unsigned val = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 t = __ldg(pat + k * 32);   // test 8*lane + k: x0, x1, y0, y1
+    for (int k = 0; k < 16; ++k) {
+        const float4 t = __ldg(pat + k * 16);   // test 16*hl + k: x0, x1, y0, y1
         const float2 px = make_float2(t.x, t.y), py = make_float2(t.z, t.w);
         const float2 xb = orbx_mul2(px, bb), ya = orbx_mul2(py, aa), xa = orbx_mul2(px, aa), yb = orbx_mul2(py, nb);
         const float2 r = orbx_add2(make_float2(__fadd_rn(xb.x, ya.x), __fadd_rn(xb.y, ya.y)), mmr);
         const float2 c = orbx_add2(make_float2(__fadd_rn(xa.x, yb.x), __fadd_rn(xa.y, yb.y)), mmc);
         const unsigned t0 = orbx_lds_u8(((unsigned)__float_as_int(r.x) << 6) + (unsigned)__float_as_int(c.x) + kreg);
         const unsigned t1 = orbx_lds_u8(((unsigned)__float_as_int(r.y) << 6) + (unsigned)__float_as_int(c.y) + kreg);
-        val |= (t0 < t1) << k;
+        val |= (unsigned)(t0 < t1) << k;
     }
 
     // ---- output slot: lapping keypoints fill from the back, the rest from the front ----
+    if (!valid) return;
     const float xs = level != 0 ? __fmul_rn(rec.x, L.sf) : rec.x;
     const float ys = level != 0 ? __fmul_rn(rec.y, L.sf) : rec.y;
     const bool lapping = xs >= (float)plan.lap0 && xs <= (float)plan.lap1;
     const int laps_before = lap_before + rec.lap_before;
     const int out_idx = lapping ? (n_total - 1 - laps_before) : (n_before + idx - laps_before);
-    if (lane == 0) recp->angle = angle;
+    if (hl == 0) recp->angle = angle;
     if (out_idx < cap_per_frame) {
         const long long orow = fo * cap_per_frame + out_idx;
-        if (desc_out) desc_out[orow * 32 + lane] = (uint8_t)val;
-        if (kps_out && lane < 7) {
+        if (desc_out) {
+            uint8_t* d = desc_out + orow * 32 + 2 * hl;
+            if (((uintptr_t)desc_out & 1) == 0) *reinterpret_cast<uint16_t*>(d) = (uint16_t)val;
+            else { d[0] = (uint8_t)val; d[1] = (uint8_t)(val >> 8); }
+        }
+        if (kps_out && hl < 7) {
             float f = xs;                                      // cv::KeyPoint: pt.x, pt.y, size, angle, response, octave, class_id
-            f = lane == 1 ? ys : f;
-            f = lane == 2 ? L.kp_size : f;
-            f = lane == 3 ? angle : f;
-            f = lane == 4 ? rec.response : f;
-            f = lane == 5 ? __int_as_float(level) : f;
-            f = lane == 6 ? __int_as_float(-1) : f;
-            reinterpret_cast<float*>(kps_out)[orow * 7 + lane] = f;
+            f = hl == 1 ? ys : f;
+            f = hl == 2 ? L.kp_size : f;
+            f = hl == 3 ? angle : f;
+            f = hl == 4 ? rec.response : f;
+            f = hl == 5 ? __int_as_float(level) : f;
+            f = hl == 6 ? __int_as_float(-1) : f;
+            reinterpret_cast<float*>(kps_out)[orow * 7 + hl] = f;
         }
     }
 }
