@@ -1305,7 +1305,7 @@ k_octree(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int level
 // blockIdx.x indexes a host-built tile table (level | tile_x << 8 | tile_y << 20).
 // TMA: the 160 x 70 byte source window arrives as one bulk tensor copy (ws.tmaps_b7, the level's plane) instead of 700 cp.async.
 template <bool TMA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 7)
 k_blur7(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, int skip_empty) {
     constexpr int SROWS = ORBX_BLUR_TH + 6;          // 70 staged rows = 35 row pairs
     constexpr int SPB = ORBX_BLUR_TW + 32;           // staged bytes per row: columns x0-16 .. x0+143 (16-byte chunks)
