@@ -427,7 +427,7 @@ int build_plan(OrbxHandle* h, int width, int height, PlanEntry** out) {
     P.ft_qcap = (int)align_up(ft_qcap, 8);
     P.ft_scap = (int)align_up(ft_scap, 8);
     P.ft_tpmagic = 0xffffffffu / (unsigned)P.ft_tp + 1u;
-    pe->ft_smem = 2 * (size_t)P.ft_tp * P.ft_trows + 2 * (size_t)P.ft_qcap;
+    pe->ft_smem = 2 * align_up((size_t)P.ft_tp * P.ft_trows, 128) + 2 * (size_t)P.ft_qcap;    // tile image + score map (128-byte aligned) + queue
     if (pe->ft_smem > 200 * 1024 || (long long)P.ft_tp * P.ft_trows > 65535) { delete pe; return fail(h, ORBX_ERR_BAD_ARGUMENT, "cell_size too large"); }
     {   // p / ft_tp by __umulhi in k_fast_tiles: exact over the tile's byte range
         const unsigned m = P.ft_tpmagic;

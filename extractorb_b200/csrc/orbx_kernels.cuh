@@ -687,8 +687,9 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     const int tp = plan.ft_tp, tpw = tp >> 2;
     const int map_bytes = tp * plan.ft_trows;                       // multiple of 16
     uint8_t* tile = smem_ft;
-    uint8_t* score = smem_ft + map_bytes;
-    uint16_t* queue = reinterpret_cast<uint16_t*>(smem_ft + 2 * map_bytes);
+    const int map_pitch = (map_bytes + 127) & ~127;                 // both maps are TMA destinations: 128-byte aligned
+    uint8_t* score = smem_ft + map_pitch;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(smem_ft + 2 * map_pitch);
     const unsigned queue_sa = (unsigned)__cvta_generic_to_shared(queue);
     const int th_rows = T.th, tw = T.tw;
     const int a16 = (ORBX_PADL + T.x0) & 15;
@@ -699,11 +700,12 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         if (tid == 0) orbx_mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
-            orbx_mbar_expect_tx(bar, (uint32_t)map_bytes);
+            // two boxes on one barrier: the tile image, and a box that lies entirely below the plane -- the copy engine fills what is
+            // outside the tensor with zeros, which clears the score map without a single store instruction
+            orbx_mbar_expect_tx(bar, 2u * (uint32_t)map_bytes);
             orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(tile), ws.tmaps + 128 * T.level, bar, ORBX_PADL + T.x0 - a16, ORBX_EDGE + T.y0, frame);
+            orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(score), ws.tmaps + 128 * T.level, bar, 0, 1 << 20, frame);
         }
-        const int nz = (th_rows * tp) >> 4;
-        for (int i = tid; i < nz; i += ORBX_FT_THREADS) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_qn = 0; s_flags = 0; }
         unsigned spins = 0;
         while (!orbx_mbar_try_wait(bar, 0)) {
