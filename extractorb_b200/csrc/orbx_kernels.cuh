@@ -697,20 +697,21 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
     // ---- stage the tile image: whole 16-byte chunks of the plane rows (64-byte aligned), score map cleared meanwhile ----
     if (TMA) {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-        if (tid == 0) orbx_mbar_init(bar, 1);
-        __syncthreads();
         if (tid == 0) {
+            orbx_mbar_init(bar, 1);                                 // init (+ its fence) and the copies come from the same thread
             // two boxes on one barrier: the tile image, and a box that lies entirely below the plane -- the copy engine fills what is
             // outside the tensor with zeros, which clears the score map without a single store instruction
             orbx_mbar_expect_tx(bar, 2u * (uint32_t)map_bytes);
             orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(tile), ws.tmaps + 128 * T.level, bar, ORBX_PADL + T.x0 - a16, ORBX_EDGE + T.y0, frame);
             orbx_tma_load_3d((uint32_t)__cvta_generic_to_shared(score), ws.tmaps + 128 * T.level, bar, 0, 1 << 20, frame);
+            s_qn = 0; s_flags = 0;
         }
-        if (tid == 0) { s_qn = 0; s_flags = 0; }
+        __syncthreads();                                            // the barrier exists (and the counters are set) before anybody polls it
         unsigned spins = 0;
         while (!orbx_mbar_try_wait(bar, 0)) {
             if (++spins > (1u << 18)) __trap();                     // a copy that never lands must fail loudly, not hang the device
         }
+        // every thread has seen the barrier complete: both maps are visible to it, no second block barrier needed
     } else {
         const uint8_t* g = ws.pyr + (long long)frame * ws.pyr_stride + L.plane_off + (long long)(ORBX_EDGE + T.y0) * L.pitch + (ORBX_PADL + T.x0 - a16);
         const int nvec = (a16 + tw + 15) >> 4;
@@ -725,8 +726,8 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         for (int i = tid; i < nz; i += ORBX_FT_THREADS) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_qn = 0; s_flags = 0; }
         __pipeline_wait_prior(0);
+        __syncthreads();
     }
-    __syncthreads();
 
     const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
     const int nrows = th_rows - 6;
