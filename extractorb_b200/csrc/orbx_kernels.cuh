@@ -1,10 +1,11 @@
 // extractorb_b200/csrc/orbx_kernels.cuh -- sm_100a kernels of the ORB extraction path.
 //
 //   k_pyr_level0 / k_pyr_resize : ComputePyramid          (reference ORBextractor.cc:1164-1219)
-//   k_fast_cells                : cell loop + cv::FAST    (:797-864)
+//   k_fast_tiles (k_fast_cells) : cell loop + cv::FAST    (:797-864); the round-1 kernel stays as an A/B reference (ORBX_FAST_V1=1)
 //   k_octree                    : DistributeOctTree       (:544-771, DivideNode :486-542)
 //   k_blur7                     : GaussianBlur 7x7 s=2    (:1126-1127)
 //   k_describe                  : IC_Angle, rBRIEF, scale-back + two-ended scatter (:75-145, :1131-1159)
+//   k_pyr_border                : copyMakeBorder of every level, only when a plane leaves the device (:1193, :1213)
 //
 // All pixel arithmetic is integer / fixed point and bit-exact with the OpenCV primitives the reference
 // calls; the float steps (fastAtan2, pattern rotation, scale-back) use __f*_rn intrinsics so that nvcc
