@@ -89,6 +89,10 @@ def main():
     kat["resize_src_111x81"] = cv2.resize(src, (111, 81), interpolation=cv2.INTER_LINEAR)
     kat["resize_nat_183x133"] = cv2.resize(nat, (183, 133), interpolation=cv2.INTER_LINEAR)
     kat["resize_nat_110x80"] = cv2.resize(nat, (110, 80), interpolation=cv2.INTER_LINEAR)   # exact 2x -> INTER_AREA path
+    kat["resize_nat_116x84"] = cv2.resize(nat, (116, 84), interpolation=cv2.INTER_LINEAR)   # scale 1.90: source steps of 1 and 2
+    kat["resize_nat_88x64"] = cv2.resize(nat, (88, 64), interpolation=cv2.INTER_LINEAR)     # scale 2.5: source steps of 2 and 3
+    kat["resize_nat_73x53"] = cv2.resize(nat, (73, 53), interpolation=cv2.INTER_LINEAR)     # scale 3.01
+    kat["resize_src_70x51"] = cv2.resize(src, (70, 51), interpolation=cv2.INTER_LINEAR)     # scale 1.90 on noise
     kat["border_src"] = cv2.copyMakeBorder(src, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
     kat["blur_src"] = cv2.GaussianBlur(src, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
     kat["blur_nat"] = cv2.GaussianBlur(nat, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
