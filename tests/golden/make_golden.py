@@ -43,6 +43,8 @@ CASES = [
     ("tum_room4_1500", "tum_room4", 1500, 1.2, 8, 20, 7, (0, 1000)),  # the README screenshot: 1420 keypoints
     ("robot866_7500_demo", "robot866", 7500, 1.2, 8, 20, 7, (0, 1000)),  # demos use 5*1500 (main_orb_extractor.cpp:43)
     ("luna_500_5lv_s15", "luna", 500, 1.5, 5, 25, 10, (0, 0)),
+    ("robot866_800_3lv_s19", "robot866", 800, 1.9, 3, 20, 7, (0, 0)),   # source columns 1 or 2 apart per destination column
+    ("luna_600_3lv_s25", "luna", 600, 2.5, 3, 20, 7, (0, 0)),           # ... 2 or 3 apart: the resize kernel's one-column pass
 ]
 
 
