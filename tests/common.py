@@ -30,6 +30,16 @@ def synth_frame(seed, w=640, h=480):
     return img.astype(np.uint8)
 
 
+def derived_images(images):
+    """Fixture images of the other BASELINE frame sizes, cut from the reference's own 640x480 robot frames (tiled
+    side by side, so no decoder or resampler is involved): KITTI 1241x376 (a width that is not a multiple of 4)
+    and EuRoC 752x480."""
+    out = dict(images)
+    out["robot866_kitti1241"] = np.ascontiguousarray(np.tile(images["robot866"], (1, 2))[52:428, :1241])
+    out["robot2196_euroc752"] = np.ascontiguousarray(np.tile(images["robot2196"], (1, 2))[:, :752])
+    return out
+
+
 def synth_batch(n, w=640, h=480, seed0=0):
     return np.stack([synth_frame(seed0 + i, w, h) for i in range(n)])
 

@@ -17,8 +17,10 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def images():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import derived_images
     with np.load(os.path.join(GOLDEN, "images.npz")) as z:
-        return {k: z[k] for k in z.files}
+        return derived_images({k: z[k] for k in z.files})
 
 
 @pytest.fixture(scope="session")

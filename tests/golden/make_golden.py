@@ -45,6 +45,8 @@ CASES = [
     ("luna_500_5lv_s15", "luna", 500, 1.5, 5, 25, 10, (0, 0)),
     ("robot866_800_3lv_s19", "robot866", 800, 1.9, 3, 20, 7, (0, 0)),   # source columns 1 or 2 apart per destination column
     ("luna_600_3lv_s25", "luna", 600, 2.5, 3, 20, 7, (0, 0)),           # ... 2 or 3 apart: the resize kernel's one-column pass
+    ("kitti1241_2000", "robot866_kitti1241", 2000, 1.2, 8, 20, 7, (0, 0)),     # BASELINE C4 geometry (tests/common.derived_images)
+    ("euroc752_1200", "robot2196_euroc752", 1200, 1.2, 8, 20, 7, (0, 0)),      # BASELINE C3 geometry
 ]
 
 
@@ -53,6 +55,9 @@ def main():
     for k, v in imgs.items():
         assert v is not None and v.dtype == np.uint8, k
     np.savez_compressed(os.path.join(HERE, "images.npz"), **imgs)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import derived_images
+    imgs = derived_images(imgs)
     for case, img, nf, sc, nl, ini, mn, lap in CASES:
         r = refio.run_reference(imgs[img], nfeatures=nf, scale=sc, nlevels=nl, ini=ini, mn=mn, lap=lap, dump_pyr=True, bump=True)[0]
         out = dict(image=np.array(img), cfg=np.array([nf, nl, ini, mn, lap[0], lap[1]], np.int64), scale=np.float32(sc),
