@@ -696,7 +696,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
             k_fast_cells<<<dim3((V.ncells + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, sl>>>(P, ws, V.cell_off,
                                                                                                                               V.cell_off + V.ncells);
         else if (V.ntiles > 0 && ws.tmaps)
-            k_fast_tiles<true><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
+            (P.ft_tp == 256 ? k_fast_tiles<true, 256> : k_fast_tiles<true, 0>)<<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         else if (V.ntiles > 0)
             k_fast_tiles<false><<<dim3(V.ntiles, nf), ORBX_FT_THREADS, pe->ft_smem, sl>>>(P, ws, V.tile_off);
         k_octree<ORBX_QT_THREADS_BIG><<<dim3(nf, 1), ORBX_QT_THREADS_BIG, pe->qt_smem, sl>>>(P, ws, l);
@@ -781,7 +781,7 @@ int launch_group_raw(OrbxHandle* h, PlanEntry* pe, cudaStream_t st, const uint8_
         if (h->fast_v1)
             k_fast_cells<<<dim3((P.ncells_total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS, nf), ORBX_FAST_WARPS * 32, pe->fast_smem, st>>>(P, ws, 0, P.ncells_total);
         else if (P.ntiles_total > 0 && ws.tmaps)
-            k_fast_tiles<true><<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
+            (P.ft_tp == 256 ? k_fast_tiles<true, 256> : k_fast_tiles<true, 0>)<<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
         else if (P.ntiles_total > 0)
             k_fast_tiles<false><<<dim3(P.ntiles_total, nf), ORBX_FT_THREADS, pe->ft_smem, st>>>(P, ws, 0);
         ++launches;
@@ -919,6 +919,7 @@ int set_kernel_attrs_device(OrbxHandle* h) {
     ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     ORBX_CUDA(raise_smem_limit(k_fast_cells, optin));
     ORBX_CUDA(raise_smem_limit(k_fast_tiles<true>, optin));
+    ORBX_CUDA(raise_smem_limit(k_fast_tiles<true, 256>, optin));
     ORBX_CUDA(raise_smem_limit(k_fast_tiles<false>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS>, optin));
     ORBX_CUDA(raise_smem_limit(k_octree<ORBX_QT_THREADS_MID>, optin));

@@ -670,7 +670,9 @@ __device__ __forceinline__ unsigned ft_queue_pair(unsigned qa, unsigned mk, int 
 
 // TMA: the tile image arrives as ONE bulk tensor copy (box = ft_tp bytes x ft_trows rows of the level's plane, described by
 // ws.tmaps[level]; columns / rows past the plane are zero-filled) instead of ~570 16-byte cp.async with their index arithmetic.
-template <bool TMA>
+// TP: the tile row pitch as a compile-time constant (256 bytes for the reference's 30-pixel cells: the ring and neighbour offsets of
+// the exact measure and the NMS become immediates, row / column of a queue entry a shift and a mask); 0 = the plan's value.
+template <bool TMA, int TP = 0>
 __global__ void __launch_bounds__(ORBX_FT_THREADS)
 k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int tile_base) {
     extern __shared__ __align__(128) uint8_t smem_ft[];
@@ -685,7 +687,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
         d[0] = __ldg(tp4); d[1] = __ldg(tp4 + 1); d[2] = __ldg(tp4 + 2);
     }
     const OrbxLevel& L = plan.lv[T.level];
-    const int tp = plan.ft_tp, tpw = tp >> 2;
+    const int tp = TP ? TP : plan.ft_tp, tpw = tp >> 2;
     const int map_bytes = tp * plan.ft_trows;                       // multiple of 16
     uint8_t* tile = smem_ft;
     const int map_pitch = (map_bytes + 127) & ~127;                 // both maps are TMA destinations: 128-byte aligned
@@ -852,7 +854,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
             if (i < na) {
                 p = queue[cbeg + i];
                 const int s = score[p];
-                const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
+                const int r = TP == 256 ? (p >> 8) : (int)__umulhi((unsigned)p, plan.ft_tpmagic);
                 const int xi = p - r * tp - a16 - 3;                         // interior column
                 const int c = (int)__umulhi((unsigned)xi, T.cmagic);
                 const int rem = xi - c * wcell;
@@ -883,7 +885,7 @@ k_fast_tiles(const __grid_constant__ OrbxPlan plan, const OrbxWs ws, const int t
                 const int slot = slot0 + i;
                 if (slot >= L.cand_cap) break;
                 const int p = queue[cbeg + i];
-                const int r = (int)__umulhi((unsigned)p, plan.ft_tpmagic);
+                const int r = TP == 256 ? (p >> 8) : (int)__umulhi((unsigned)p, plan.ft_tpmagic);
                 const int x = p - r * tp - a16;                              // tile image column (>= 3)
                 const int c = (int)__umulhi((unsigned)(x - 3), T.cmagic);
                 const int xc = x - c * wcell;                                // column inside the cell image
